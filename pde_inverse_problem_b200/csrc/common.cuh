@@ -1,0 +1,60 @@
+// common.cuh — error plumbing and small device helpers shared by all pdeip kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pdeip.h"
+
+namespace pdeip {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define PDEIP_REQUIRE(cond, code, ...)            \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::pdeip::set_error(__VA_ARGS__);            \
+      return (code);                              \
+    }                                             \
+  } while (0)
+
+#define PDEIP_CUDA_OK(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::pdeip::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                       \
+      return PDEIP_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+#define PDEIP_LAUNCH_OK()                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      ::pdeip::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),       \
+                         __FILE__, __LINE__);                                              \
+      return PDEIP_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// element (point n, component c) of a [n][dim] (AOS) or [dim][n] (SOA) array
+__device__ __forceinline__ int64_t elem_index(int layout, int64_t n, int c, int64_t n_total, int dim) {
+  return layout == PDEIP_LAYOUT_AOS ? n * dim + c : (int64_t)c * n_total + n;
+}
+
+}  // namespace pdeip

@@ -1,0 +1,341 @@
+// integrator.cu — K1: fused multi-step kinetic-Langevin (Euler–Maruyama) integrator.
+//
+// Replaces utils/sampling_utils.py:6-52 (update_step + the vmapped lax.scan).  One thread owns one
+// particle for the whole trajectory: (q,p) stay in registers across all S+1 steps, the noise is
+// drawn in registers from Philox4x32-10 (or read from an injected tensor for parity runs), the
+// drift functor is inlined, and the only HBM traffic is the initial state read, the emitted
+// trajectory samples and the final state — 2d*4 bytes per emitted particle-step.
+#include "common.cuh"
+#include "drift.cuh"
+#include "philox.cuh"
+
+namespace pdeip {
+
+struct IntegrateArgs {
+  const float* z0;
+  float* z_last;
+  float* traj;
+  float* tau;
+  int64_t n;
+  int d;
+  int n_steps;
+  float dt;
+  float gamma;
+  const float* drift_params;
+  int n_gaussian;
+  float inv_sigma2;
+  const float* noise;
+  const float* tau0;
+  uint64_t seed;
+  uint64_t particle_offset;
+  uint32_t step_offset;
+  int schedule;
+  int state_layout;
+  int traj_layout;
+  int emit_every;
+  int emit_offset;
+  int s_emit;  // number of emitted samples
+};
+
+template <int DP>
+__device__ __forceinline__ void emit_state(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
+                                           int d, int s_e, int s_emit, const float (&q)[DP],
+                                           const float (&p)[DP]) {
+  const int two_d = 2 * d;
+  if (layout == PDEIP_TRAJ_TIME_SOA) {
+    float* o = base + (int64_t)s_e * two_d * n_total + n;
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) {
+        __stcs(o + (int64_t)i * n_total, q[i]);
+        __stcs(o + (int64_t)(d + i) * n_total, p[i]);
+      }
+    return;
+  }
+  float* o = (layout == PDEIP_TRAJ_PARTICLE_MAJOR) ? base + (n * s_emit + s_e) * two_d
+                                                    : base + ((int64_t)s_e * n_total + n) * two_d;
+  if (DP % 4 == 0 && d == DP) {
+#pragma unroll
+    for (int i4 = 0; i4 < DP / 4; ++i4) {
+      __stcs(reinterpret_cast<float4*>(o) + i4, make_float4(q[4 * i4], q[4 * i4 + 1], q[4 * i4 + 2], q[4 * i4 + 3]));
+      __stcs(reinterpret_cast<float4*>(o + d) + i4,
+             make_float4(p[4 * i4], p[4 * i4 + 1], p[4 * i4 + 2], p[4 * i4 + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) {
+        o[i] = q[i];
+        o[d + i] = p[i];
+      }
+  }
+}
+
+template <int DP, int DRIFT>
+__global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  // stage the drift parameters (zero-padded to DP) in shared memory
+  float* A_s = smem;           // LINEAR / MEANFIELD: [DP][DP] (+ [DP] shift)
+  float* shift_s = nullptr;
+  if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+    load_padded<DP>(A_s, a.drift_params, a.d, a.d, threadIdx.x, blockDim.x);
+    // rows >= d must be zero too
+    for (int idx = a.d * DP + threadIdx.x; idx < DP * DP; idx += blockDim.x) A_s[idx] = 0.0f;
+    if constexpr (DRIFT == PDEIP_DRIFT_MEANFIELD) {
+      shift_s = smem + DP * DP;
+      for (int i = threadIdx.x; i < DP; i += blockDim.x)
+        shift_s[i] = i < a.d ? a.drift_params[a.d * a.d + i] : 0.0f;
+    }
+  } else if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
+    load_padded<DP>(smem, a.drift_params, a.n_gaussian, a.d, threadIdx.x, blockDim.x);
+  }
+  __syncthreads();
+
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n) return;
+  const int d = a.d;
+  const uint64_t pid = a.particle_offset + (uint64_t)n;
+
+  float q[DP], p[DP];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) {
+    q[i] = (i < d) ? a.z0[elem_index(a.state_layout, n, i, a.n, 2 * d)] : 0.0f;
+    p[i] = (i < d) ? a.z0[elem_index(a.state_layout, n, d + i, a.n, 2 * d)] : 0.0f;
+  }
+
+  const bool ref_sched = (a.schedule == PDEIP_SCHEDULE_REFERENCE);
+  float t0 = 0.0f;
+  if (ref_sched) {
+    t0 = a.tau0 ? a.tau0[n] : philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
+  }
+  const int total_steps = ref_sched ? a.n_steps + 1 : a.n_steps;
+  const int n_draws = total_steps;
+
+  for (int s = 0; s < total_steps; ++s) {
+    float h = a.dt;
+    if (ref_sched) {
+      if (s == 0) h = t0;                        // sampling_utils.py:33
+      else if (s == a.n_steps) h = a.dt - t0;    // sampling_utils.py:45-46
+    }
+    // drift
+    float g[DP];
+    if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
+      gmm_grad_thread<DP>(q, smem, a.n_gaussian, a.inv_sigma2, g);
+    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+      linear_grad_thread<DP>(q, A_s, shift_s, g);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DP; ++i) g[i] = 0.0f;
+    }
+    // noise
+    float xi[DP];
+    if (a.noise) {
+      const float* nz = a.noise + (n * n_draws + s) * d;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) xi[i] = (i < d) ? nz[i] : 0.0f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < (DP + 3) / 4; ++j) {
+        float r4[4];
+        philox_normal4(a.seed, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * j + k < DP) xi[4 * j + k] = (4 * j + k < d) ? r4[k] : 0.0f;
+      }
+    }
+    // p' = p - h g + sqrt(h) sqrt(2) xi - gamma p h ;  q' = q + h p'     (sampling_utils.py:14-20)
+    const float sq = sqrtf(h) * 1.41421356237309515f;
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      const float pn = p[i] - h * g[i] + sq * xi[i] - a.gamma * p[i] * h;
+      p[i] = pn;
+      q[i] = q[i] + h * pn;
+    }
+    // emission: REFERENCE schedule emits samples 0..S-1 (the last step only feeds z_last);
+    // UNIFORM schedule emits every state.
+    const bool is_sample = ref_sched ? (s < a.n_steps) : true;
+    if (a.traj && is_sample && (s % a.emit_every) == a.emit_offset) {
+      emit_state<DP>(a.traj, a.traj_layout, n, a.n, d, s / a.emit_every, a.s_emit, q, p);
+    }
+  }
+  if (a.z_last) {
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) {
+        a.z_last[elem_index(a.state_layout, n, i, a.n, 2 * d)] = q[i];
+        a.z_last[elem_index(a.state_layout, n, d + i, a.n, 2 * d)] = p[i];
+      }
+  }
+  if (a.tau && ref_sched) {
+    for (int s = 0; s < a.n_steps; ++s) a.tau[n * a.n_steps + s] = t0 + (float)s * a.dt;  // :48
+  }
+}
+
+template <int DP>
+static int launch_integrate(const IntegrateArgs& a, int drift_kind, cudaStream_t st) {
+  const int block = 128;
+  const int64_t grid = (a.n + block - 1) / block;
+  size_t smem = 0;
+  switch (drift_kind) {
+    case PDEIP_DRIFT_NONE:
+      kl_integrate_kernel<DP, PDEIP_DRIFT_NONE><<<(unsigned)grid, block, 0, st>>>(a);
+      break;
+    case PDEIP_DRIFT_LINEAR:
+      smem = sizeof(float) * DP * DP;
+      kl_integrate_kernel<DP, PDEIP_DRIFT_LINEAR><<<(unsigned)grid, block, smem, st>>>(a);
+      break;
+    case PDEIP_DRIFT_MEANFIELD:
+      smem = sizeof(float) * (DP * DP + DP);
+      kl_integrate_kernel<DP, PDEIP_DRIFT_MEANFIELD><<<(unsigned)grid, block, smem, st>>>(a);
+      break;
+    case PDEIP_DRIFT_GMM:
+      smem = sizeof(float) * (size_t)a.n_gaussian * DP;
+      PDEIP_REQUIRE(smem <= 48 * 1024, PDEIP_ERR_UNSUPPORTED, "GMM centres exceed 48 KB of shared memory");
+      kl_integrate_kernel<DP, PDEIP_DRIFT_GMM><<<(unsigned)grid, block, smem, st>>>(a);
+      break;
+    default:
+      PDEIP_REQUIRE(false, PDEIP_ERR_INVALID_ARG, "unknown drift kind %d", drift_kind);
+  }
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// noise dumps (what the integrator draws in Philox mode) and the Gaussian initial ensemble
+// ------------------------------------------------------------------------------------------
+__global__ void philox_normals_kernel(float* out, int64_t n, int n_draws, int d, uint64_t seed,
+                                      uint64_t particle_offset, uint32_t step_offset) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (particle, draw)
+  if (idx >= n * n_draws) return;
+  const int64_t p = idx / n_draws;
+  const int s = (int)(idx - p * n_draws);
+  for (int j = 0; j < (d + 3) / 4; ++j) {
+    float r4[4];
+    philox_normal4(seed, particle_offset + (uint64_t)p, step_offset + (uint32_t)s, (uint32_t)j, r4);
+    for (int k = 0; k < 4; ++k)
+      if (4 * j + k < d) out[idx * d + 4 * j + k] = r4[k];
+  }
+}
+
+__global__ void philox_uniforms_kernel(float* out, int64_t n, uint64_t seed, uint64_t particle_offset) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = philox_uniform01(seed, particle_offset + (uint64_t)p, kTagTau0);
+}
+
+__global__ void philox_raw_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c0 = ctr[4 * i], c1 = ctr[4 * i + 1], c2 = ctr[4 * i + 2], c3 = ctr[4 * i + 3];
+  philox4x32_10(c0, c1, c2, c3, key[0], key[1]);
+  out[4 * i] = c0; out[4 * i + 1] = c1; out[4 * i + 2] = c2; out[4 * i + 3] = c3;
+}
+
+// z = mu + cov_half xi   (core/distribution.py:64-65); one thread per sample, dim <= 64
+__global__ void gaussian_sample_kernel(float* out, int64_t n, int dim, const float* __restrict__ mu,
+                                       const float* __restrict__ cov_half, uint64_t seed,
+                                       uint64_t particle_offset, int layout) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float xi[64];
+  for (int j = 0; j < (dim + 3) / 4; ++j) {
+    float r4[4];
+    philox_normal4(seed, particle_offset + (uint64_t)p, kTagInit, (uint32_t)j, r4);
+    for (int k = 0; k < 4; ++k) xi[4 * j + k] = r4[k];
+  }
+  for (int i = 0; i < dim; ++i) {
+    float s = mu ? mu[i] : 0.0f;
+    if (cov_half) {
+      for (int k = 0; k < dim; ++k) s = fmaf(cov_half[i * dim + k], xi[k], s);
+    } else {
+      s += xi[i];
+    }
+    out[elem_index(layout, p, i, n, dim)] = s;
+  }
+}
+
+}  // namespace pdeip
+
+using namespace pdeip;
+
+extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
+                                  int64_t n_particles, int d, int n_steps, float dt, float gamma,
+                                  int drift_kind, const float* drift_params, int n_gaussian, float sigma,
+                                  const float* noise, const float* tau0, uint64_t seed,
+                                  uint64_t particle_offset, uint32_t step_offset, int schedule,
+                                  int state_layout, int traj_layout, int emit_every, int emit_offset,
+                                  void* stream) {
+  PDEIP_REQUIRE(z0 != nullptr, PDEIP_ERR_INVALID_ARG, "z0 is NULL");
+  PDEIP_REQUIRE(n_particles >= 0 && d >= 1 && d <= 32, PDEIP_ERR_UNSUPPORTED,
+                "integrator supports 1 <= d <= 32 (got d=%d)", d);
+  PDEIP_REQUIRE(n_steps >= 1, PDEIP_ERR_INVALID_ARG, "n_steps must be >= 1");
+  PDEIP_REQUIRE(schedule == PDEIP_SCHEDULE_REFERENCE || schedule == PDEIP_SCHEDULE_UNIFORM,
+                PDEIP_ERR_INVALID_ARG, "unknown schedule %d", schedule);
+  PDEIP_REQUIRE(state_layout == PDEIP_LAYOUT_AOS || state_layout == PDEIP_LAYOUT_SOA, PDEIP_ERR_INVALID_ARG,
+                "unknown state layout %d", state_layout);
+  PDEIP_REQUIRE(traj_layout >= 0 && traj_layout <= 2, PDEIP_ERR_INVALID_ARG, "unknown trajectory layout %d",
+                traj_layout);
+  PDEIP_REQUIRE(emit_every >= 1 && emit_offset >= 0 && emit_offset < emit_every, PDEIP_ERR_INVALID_ARG,
+                "emit_every/emit_offset out of range");
+  PDEIP_REQUIRE(drift_kind == PDEIP_DRIFT_NONE || drift_params != nullptr, PDEIP_ERR_INVALID_ARG,
+                "drift_params is NULL");
+  PDEIP_REQUIRE(drift_kind != PDEIP_DRIFT_GMM || (n_gaussian >= 1 && sigma > 0.0f), PDEIP_ERR_INVALID_ARG,
+                "GMM drift needs n_gaussian >= 1 and sigma > 0");
+  if (n_particles == 0) return PDEIP_OK;
+  IntegrateArgs a;
+  a.z0 = z0; a.z_last = z_last; a.traj = traj; a.tau = tau; a.n = n_particles; a.d = d;
+  a.n_steps = n_steps; a.dt = dt; a.gamma = gamma; a.drift_params = drift_params;
+  a.n_gaussian = n_gaussian; a.inv_sigma2 = drift_kind == PDEIP_DRIFT_GMM ? 1.0f / (sigma * sigma) : 1.0f;
+  a.noise = noise; a.tau0 = tau0; a.seed = seed; a.particle_offset = particle_offset;
+  a.step_offset = step_offset; a.schedule = schedule; a.state_layout = state_layout;
+  a.traj_layout = traj_layout; a.emit_every = emit_every; a.emit_offset = emit_offset;
+  const int n_samples = n_steps;  // both schedules expose n_steps samples
+  a.s_emit = (n_samples - emit_offset + emit_every - 1) / emit_every;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 2) return launch_integrate<2>(a, drift_kind, st);
+  if (d <= 4) return launch_integrate<4>(a, drift_kind, st);
+  if (d <= 8) return launch_integrate<8>(a, drift_kind, st);
+  if (d <= 16) return launch_integrate<16>(a, drift_kind, st);
+  return launch_integrate<32>(a, drift_kind, st);
+}
+
+extern "C" int pdeip_philox_normals(float* out, int64_t n_particles, int n_draws, int d, uint64_t seed,
+                                    uint64_t particle_offset, uint32_t step_offset, void* stream) {
+  PDEIP_REQUIRE(out && n_particles >= 0 && n_draws >= 1 && d >= 1, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  const int64_t total = n_particles * n_draws;
+  if (total == 0) return PDEIP_OK;
+  philox_normals_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      out, n_particles, n_draws, d, seed, particle_offset, step_offset);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+extern "C" int pdeip_philox_uniforms(float* out, int64_t n_particles, uint64_t seed, uint64_t particle_offset,
+                                     void* stream) {
+  PDEIP_REQUIRE(out && n_particles >= 0, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  if (n_particles == 0) return PDEIP_OK;
+  philox_uniforms_kernel<<<(unsigned)((n_particles + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      out, n_particles, seed, particle_offset);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+extern "C" int pdeip_philox_raw(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n,
+                                void* stream) {
+  PDEIP_REQUIRE(ctr && key && out && n >= 0, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  if (n == 0) return PDEIP_OK;
+  philox_raw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctr, key, out, n);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+extern "C" int pdeip_gaussian_sample(float* out, int64_t n, int dim, const float* mu, const float* cov_half,
+                                     uint64_t seed, uint64_t particle_offset, int layout, void* stream) {
+  PDEIP_REQUIRE(out && n >= 0 && dim >= 1 && dim <= 64, PDEIP_ERR_UNSUPPORTED,
+                "gaussian_sample supports 1 <= dim <= 64 (got %d)", dim);
+  PDEIP_REQUIRE(layout == PDEIP_LAYOUT_AOS || layout == PDEIP_LAYOUT_SOA, PDEIP_ERR_INVALID_ARG, "bad layout");
+  if (n == 0) return PDEIP_OK;
+  gaussian_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      out, n, dim, mu, cov_half, seed, particle_offset, layout);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}

@@ -1,0 +1,213 @@
+"""GPU parity: K1 integrator and K2 drifts through the C ABI vs the oracle (injected noise)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import relmax
+from oracle import integrator as o_int
+from oracle import moments as o_mom
+from oracle import philox as o_philox
+from oracle import potential as o_pot
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from pde_inverse_problem_b200 import ops, _lib
+    return ops, _lib
+
+
+@pytest.mark.parametrize("d,K", [(2, 3), (4, 3), (8, 16), (5, 7), (32, 64)])
+def test_gmm_grad_matches_oracle(cuda, d, K):
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(d * 100 + K)
+    x = torch.randn(4099, d, generator=g, dtype=torch.float64) * 2.0
+    mus = torch.rand(K, d, generator=g, dtype=torch.float64) * 8 - 4
+    ref_g = o_pot.vg_gmm_V(x, mus, 1.0)
+    ref_v = o_pot.GMMPotential(mus, 1.0).value(x)
+    val, grd = ops.gmm_value_grad(x.float().to(cuda), mus.float().to(cuda), 1.0, want_value=True)
+    assert relmax(grd, ref_g) < 1e-5  # fp32 path, BASELINE.json rtol 1e-5 (max-norm metric)
+    assert relmax(val, ref_v) < 1e-5
+
+
+def test_gmm_single_gaussian_is_x_minus_mu(cuda):
+    ops, L = _ops()
+    x = torch.randn(1000, 8, device=cuda)
+    mu = torch.randn(1, 8, device=cuda)
+    _, grd = ops.gmm_value_grad(x, mu, 1.0)
+    assert relmax(grd, x - mu) < 1e-6  # KAT-3, K = 1
+
+
+def test_linear_grad(cuda):
+    ops, L = _ops()
+    x = torch.randn(3001, 16, dtype=torch.float64)
+    A = torch.randn(16, 16, dtype=torch.float64)
+    out = ops.linear_grad(x.float().to(cuda), A.float().to(cuda))
+    assert relmax(out, x @ A.T) < 1e-5
+
+
+def test_philox_raw_known_answers(cuda):
+    """Random123 known-answer vectors for Philox4x32-10 (bit-exact)."""
+    ops, L = _ops()
+    def i32(v):
+        return np.array(v, dtype=np.uint32).view(np.int32)
+    cases = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+             ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+              (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in cases:
+        out = ops.philox_raw(torch.from_numpy(i32([ctr])).to(cuda), torch.from_numpy(i32(key)).to(cuda))
+        got = out.cpu().numpy().view(np.uint32)[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_philox_normals_match_numpy_restatement(cuda):
+    ops, L = _ops()
+    n, draws, d, seed, off = 513, 3, 8, 0x1234567890ABCDEF, 7
+    dev = ops.philox_normals(n, draws, d, seed, particle_offset=off, step_offset=5).cpu().double().numpy()
+    for s in range(draws):
+        ref = o_philox.normals(seed, np.arange(n) + off, 5 + s, d)
+        assert np.abs(dev[:, s] - ref).max() < 2e-5  # fast-math log/sincos on device
+    u = ops.philox_uniforms(n, seed, particle_offset=off).cpu().double().numpy()
+    assert np.array_equal(u, o_philox.uniform01(seed, np.arange(n) + off))  # exact
+
+
+def _setup_traj(d, K, N, S, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    z0 = torch.randn(N, 2 * d, generator=g, dtype=torch.float64)
+    noise = torch.randn(N, S + 1, d, generator=g, dtype=torch.float64)
+    tau0 = torch.rand(N, generator=g, dtype=torch.float64)
+    mus = torch.rand(K, d, generator=g, dtype=torch.float64) * 8 - 4
+    return z0, noise, tau0, mus
+
+
+@pytest.mark.parametrize("d", [2, 4, 8, 16])
+def test_single_step_gmm_rtol_1e5(cuda, d):
+    """Parity protocol (i): one reference trajectory with S = 1 (two update_steps) from identical states."""
+    ops, L = _ops()
+    N, S, dt, gamma = 2053, 1, 0.01, 0.5
+    z0, noise, tau0, mus = _setup_traj(d, 5, N, S, seed=d)
+    tau0 = tau0 * dt
+    pot = o_pot.GMMPotential(mus, 1.0)
+    last, traj, tau = o_int.underdamped_langevin_dynamics_scan(z0, S, dt, noise, tau0, pot.gradient, gamma)
+    zl, tr, ta = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_GMM, mus.float().to(cuda),
+                                  n_gaussian=5, sigma=1.0, noise=noise.float().to(cuda),
+                                  tau0=tau0.float().to(cuda), want_tau=True)
+    assert relmax(zl, last) < 1e-5
+    assert relmax(tr, traj) < 1e-5
+    assert relmax(ta, tau) < 1e-6
+
+
+@pytest.mark.parametrize("d", [4, 16])
+def test_full_trajectory_linear_drift_rtol_1e5(cuda, d):
+    """Parity protocol (iii): contractive linear (OU) drift holds rtol 1e-5 over the whole trajectory."""
+    ops, L = _ops()
+    N, S, T, gamma = 1500, 100, 2.0, 1.0
+    dt = T / S
+    z0, noise, tau0, _ = _setup_traj(d, 1, N, S, seed=3)
+    tau0 = tau0 * dt
+    cfg = o_mom.kinetic_ou_configuration(d)
+    F = torch.as_tensor(cfg["tilde_F"]) / d  # keep dt * |F| well inside the stability region
+    drift = o_pot.LinearDrift(F)
+    last, traj, _ = o_int.underdamped_langevin_dynamics_scan(z0, S, dt, noise, tau0, drift.gradient, gamma)
+    for layout in (L.TRAJ_PARTICLE_MAJOR, L.TRAJ_TIME_MAJOR, L.TRAJ_TIME_SOA):
+        zl, tr, _ = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_LINEAR, F.float().to(cuda),
+                                     noise=noise.float().to(cuda), tau0=tau0.float().to(cuda),
+                                     traj_layout=layout)
+        if layout == L.TRAJ_TIME_MAJOR:
+            tr = tr.permute(1, 0, 2)
+        elif layout == L.TRAJ_TIME_SOA:
+            tr = tr.permute(2, 0, 1)
+        assert relmax(zl, last) < 1e-5
+        assert relmax(tr, traj) < 1e-5
+
+
+def test_multi_step_gmm_within_fp32_twin_band(cuda):
+    """Parity protocol (ii): GMM trajectories are locally unstable, so the GPU error vs the float64 oracle is
+    compared with the error of the CPU fp32 twin of the same code: within 2x (plus a floor)."""
+    ops, L = _ops()
+    d, K, N, S, T, gamma = 8, 16, 4096, 200, 2.0, 0.5
+    dt = T / S
+    z0, noise, tau0, mus = _setup_traj(d, K, N, S, seed=11)
+    z0[:, :d] *= 2.0
+    z0[:, d:] *= math.sqrt(0.1)
+    tau0 = tau0 * dt
+    last64, traj64, _ = o_int.underdamped_langevin_dynamics_scan(
+        z0, S, dt, noise, tau0, o_pot.GMMPotential(mus, 1.0).gradient, gamma)
+    last32, traj32, _ = o_int.underdamped_langevin_dynamics_scan(
+        z0.float(), S, dt, noise.float(), tau0.float(), o_pot.GMMPotential(mus.float(), 1.0).gradient, gamma)
+    zl, tr, _ = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_GMM, mus.float().to(cuda),
+                                 n_gaussian=K, noise=noise.float().to(cuda), tau0=tau0.float().to(cuda))
+    err_gpu = (tr.cpu().double() - traj64).abs()
+    err_twin = (traj32.double() - traj64).abs()
+    scale = traj64.abs().max().item()
+    for s in (0, 9, 99, 199):
+        g_max, t_max = err_gpu[:, s].max().item() / scale, err_twin[:, s].max().item() / scale
+        g_med, t_med = err_gpu[:, s].median().item(), err_twin[:, s].median().item()
+        assert g_max <= 2.0 * t_max + 1e-6, (s, g_max, t_max)
+        assert g_med <= 2.0 * t_med + 1e-7, (s, g_med, t_med)
+    assert relmax(tr[:, 0], traj64[:, 0]) < 1e-5  # first sample: strict
+
+
+def test_emit_every_and_soa_state(cuda):
+    ops, L = _ops()
+    d, N, S, dt, gamma = 4, 777, 20, 0.05, 1.0
+    z0, noise, tau0, _ = _setup_traj(d, 1, N, S, seed=5)
+    tau0 = tau0 * dt
+    F = torch.eye(d, dtype=torch.float64) * 0.7
+    last, traj, _ = o_int.underdamped_langevin_dynamics_scan(z0, S, dt, noise, tau0, o_pot.LinearDrift(F).gradient, gamma)
+    zl, tr, _ = ops.kl_integrate(z0.float().t().contiguous().to(cuda), S, dt, gamma, L.DRIFT_LINEAR, F.float().to(cuda),
+                                 noise=noise.float().to(cuda), tau0=tau0.float().to(cuda),
+                                 state_layout=L.LAYOUT_SOA, traj_layout=L.TRAJ_TIME_SOA, emit_every=5, emit_offset=2)
+    assert relmax(zl.t(), last) < 1e-5
+    assert tr.shape == (4, 2 * d, N)
+    assert relmax(tr.permute(2, 0, 1), traj[:, 2::5]) < 1e-5
+
+
+def test_philox_mode_equals_injected_device_noise(cuda):
+    """The in-register Philox path and the injected-noise path run the same arithmetic."""
+    ops, L = _ops()
+    d, N, S, dt, gamma, seed = 8, 1000, 10, 0.01, 0.5, 99
+    z0, _, _, mus = _setup_traj(d, 4, N, S, seed=8)
+    z0 = z0.float().to(cuda)
+    mus = mus.float().to(cuda)
+    noise = ops.philox_normals(N, S + 1, d, seed)
+    tau0 = ops.philox_uniforms(N, seed) * dt
+    a = ops.kl_integrate(z0, S, dt, gamma, L.DRIFT_GMM, mus, n_gaussian=4, seed=seed)
+    b = ops.kl_integrate(z0, S, dt, gamma, L.DRIFT_GMM, mus, n_gaussian=4, noise=noise, tau0=tau0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # sharding invariance: the second half computed with particle_offset reproduces the same particles
+    c = ops.kl_integrate(z0[N // 2:].contiguous(), S, dt, gamma, L.DRIFT_GMM, mus, n_gaussian=4, seed=seed,
+                         particle_offset=N // 2)
+    assert torch.equal(c[0], a[0][N // 2:])
+
+
+def test_ou_ensemble_moments_match_discrete_recursion(cuda):
+    """KAT-2 / KAT-1 at config C2 scale-down: kinetic OU, d=4, S=100, dt=0.02, uniform schedule (tau0 = 0)."""
+    ops, L = _ops()
+    d, N, S, T = 4, 1 << 19, 100, 2.0
+    dt = T / S
+    cfg = o_mom.kinetic_ou_configuration(d)
+    cfg["tilde_F"] = cfg["tilde_F"] / 4.0  # dt * lambda_max well inside the stability region
+    Z, I = np.zeros((d, d)), np.eye(d)
+    cfg["F"] = np.block([[Z, I], [-cfg["tilde_F"], -cfg["gamma_friction"] * I]])
+    z0 = ops.gaussian_sample(N, 2 * d, None, None, seed=5)
+    zl, _, _ = ops.kl_integrate(z0, S, dt, cfg["gamma_friction"], L.DRIFT_LINEAR,
+                                torch.as_tensor(cfg["tilde_F"], dtype=torch.float32, device=cuda),
+                                seed=17, schedule=L.SCHEDULE_UNIFORM, want_traj=False)
+    s1, s2 = ops.ensemble_moments(zl)
+    mean = (s1 / N).cpu().double().numpy()
+    cov = (s2 / N).cpu().double().numpy() - np.outer(mean, mean)
+    m_d, P_d = o_mom.discrete_mean_cov(S, dt, cfg, tau0=0.0)  # S-1 steps of dt plus (0, dt): S steps of dt
+    m_c, P_c = o_mom.lyapunov_mean_cov(T, cfg)
+    rel_d = np.linalg.norm(cov - P_d) / np.linalg.norm(P_d)
+    rel_c = np.linalg.norm(cov - P_c) / np.linalg.norm(P_c)
+    gap = np.linalg.norm(P_d - P_c) / np.linalg.norm(P_c)
+    assert rel_d < 1e-2, rel_d                  # Monte-Carlo error at N = 2^19 (~0.4 %)
+    assert np.abs(mean - m_d).max() < 1e-2
+    assert abs(rel_c - gap) < 1e-2              # same O(dt) bias to the continuous solution as the scheme itself
+    # moments kernel vs torch
+    zc = zl.double()
+    assert relmax(s2, (zc.T @ zc)) < 1e-4
