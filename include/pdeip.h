@@ -44,7 +44,7 @@ extern "C" {
 /* trajectory layouts of pdeip_kl_integrate */
 #define PDEIP_TRAJ_PARTICLE_MAJOR 0 /* [N][S_emit][2d]  (reference: utils/sampling_utils.py:52 under vmap) */
 #define PDEIP_TRAJ_TIME_MAJOR     1 /* [S_emit][N][2d] */
-#define PDEIP_TRAJ_TIME_SOA       2 /* [S_emit][2d][N] */
+#define PDEIP_TRAJ_TIME_SOA       2 /* [2d][S_emit][N]: an SOA point set of S_emit*N points, point = s*N + n */
 
 /* drift kinds */
 #define PDEIP_DRIFT_NONE      0 /* VoidPotential, core/potential.py:27-29 */
@@ -120,6 +120,19 @@ int pdeip_philox_raw(const uint32_t* ctr, const uint32_t* key, uint32_t* out, in
  * out [N][dim] AOS or [dim][N] SOA; cov_half row-major [dim][dim] (NULL -> identity); mu NULL -> 0 */
 int pdeip_gaussian_sample(float* out, int64_t n, int dim, const float* mu, const float* cov_half,
                           uint64_t seed, uint64_t particle_offset, int layout, void* stream);
+
+/* exact samplers feeding the residual in "online / exact" mode.
+ * grouped: sample p of group g = p / per_group is mus[g] + cov_halves[g] xi    (mus [G][dim], cov_halves
+ *   [G][dim][dim]; replaces Gaussian(mean_t, cov_t).sample per time stamp,
+ *   example_problems/kinetic_fokker_planck_example_OU.py:140-190);  out [G*per_group][dim].
+ * ou_exact: overdamped OU at a per-sample random time t ~ U(t_min, t_max), closed form in the eigenbasis of F
+ *   (example_problems/fokker_planck_example.py:48-55,84-96): U [d][d], s [d], B0 = U^T P0 U, B = U^T L U,
+ *   mt0 = U^T m0;  out [n][d], out_t [n] (nullable). */
+int pdeip_gaussian_sample_grouped(float* out, int64_t n_groups, int per_group, int dim, const float* mus,
+                                  const float* cov_halves, uint64_t seed, uint64_t particle_offset, void* stream);
+int pdeip_ou_exact_sample(float* out, float* out_t, int64_t n, int d, const float* U, const float* s,
+                          const float* B0, const float* B, const float* mt0, float t_min, float t_max,
+                          uint64_t seed, uint64_t particle_offset, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  GMM potential value / gradient.       replaces core/potential.py:32-61

@@ -179,3 +179,45 @@ def fp_value_and_grad(params, data, T: float, grad_true_0T: Optional[torch.Tenso
         res["loss ground truth"] = ((grad_true_0T - g0T) ** 2).sum(-1).mean()
     res["loss"] = loss
     return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# parametric models (closed forms of SURVEY.md §9.5), checked against autodiff in tests/test_oracle_kat.py
+# ---------------------------------------------------------------------------------------------------
+def gmm_param_point_set(mus, y, v, alpha: float, beta: float, c_g: float, scale: float):
+    """V = -logsumexp(-|y - mu_k|^2 / 2) with learnable mus (GMM.py:214-234).
+    l = alpha D_v^2 V + beta D_v V + c_g |grad V|^2.  Returns (sum l * scale, dmus, g, D1, D2)."""
+    r = y[:, None, :] - mus[None]                      # [N,K,d]
+    a = -0.5 * (r * r).sum(-1)
+    w = torch.softmax(a, dim=1)                        # [N,K]
+    g = (w[..., None] * r).sum(1)                      # E[r]
+    c = (r * v[:, None, :]).sum(-1)                    # c_k = r_k . v
+    Ec = (w * c).sum(1, keepdim=True)
+    Ec2 = (w * c * c).sum(1, keepdim=True)
+    D1 = Ec[:, 0]
+    D2 = (v * v).sum(-1) - (Ec2[:, 0] - Ec[:, 0] ** 2)
+    cg = (r * g[:, None, :]).sum(-1)
+    Ecg = (w * cg).sum(1, keepdim=True)
+    beta_g = 2.0 * c_g
+    # d/dmu_k D_u V (u const) = -w_k u + w_k (c^u_k - E[c^u]) r_k
+    # d/dmu_k D_v^2 V = 2 w_k c_k v - w_k (c_k^2 - E[c^2]) r_k + 2 E[c] (-w_k v + w_k (c_k - E[c]) r_k)
+    s_g = -beta_g * w                                                       # coefficient of g
+    s_v = -beta * w + alpha * (2 * w * c - 2 * Ec * w)                      # coefficient of v
+    s_r = (beta_g * w * (cg - Ecg) + beta * w * (c - Ec)
+           + alpha * (-w * (c * c - Ec2) + 2 * Ec * w * (c - Ec)))          # coefficient of r_k
+    dmus = s_g.T @ g + s_v.T @ v + s_r.T @ y - mus * s_r.sum(0)[:, None]
+    total = alpha * D2 + beta * D1 + c_g * (g * g).sum(-1)
+    return scale * total.sum(), scale * dmus, g, D1, D2
+
+
+def quad_param_point_set(W, b, y, v, alpha: float, beta: float, c_g: float, scale: float):
+    """V = y.(yW + b) (OU.py:209-220; Flax Dense kernel W[in,out]).  grad V = (W + W^T) y + b,
+    D_v V = grad V . v, D_v^2 V = 2 v^T W v."""
+    g = y @ (W + W.T).T + b
+    D1 = (g * v).sum(-1)
+    D2 = 2 * ((v @ W) * v).sum(-1)
+    # d|g|^2/dW_ij = 2 (g_i y_j + g_j y_i); d(v^T W v)/dW_ij = v_i v_j; d(g.v)/dW_ij = v_i y_j + v_j y_i
+    dW = c_g * 2 * (g.T @ y + y.T @ g) + alpha * 2 * (v.T @ v) + beta * (v.T @ y + y.T @ v)
+    db = c_g * 2 * g.sum(0) + beta * v.sum(0)
+    total = alpha * D2 + beta * D1 + c_g * (g * g).sum(-1)
+    return scale * total.sum(), scale * dW, scale * db, g, D1, D2

@@ -51,6 +51,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_philox_uniforms": (_i, [_p, _l, _u64, _u64, _p]),
     "pdeip_philox_raw": (_i, [_p, _p, _p, _l, _p]),
     "pdeip_gaussian_sample": (_i, [_p, _l, _i, _p, _p, _u64, _u64, _i, _p]),
+    "pdeip_gaussian_sample_grouped": (_i, [_p, _l, _i, _i, _p, _p, _u64, _u64, _p]),
+    "pdeip_ou_exact_sample": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _f, _f, _u64, _u64, _p]),
     "pdeip_gmm_value_grad": (_i, [_p, _p, _i, _f, _p, _p, _l, _i, _p]),
     "pdeip_linear_grad": (_i, [_p, _p, _p, _l, _i, _p]),
     "pdeip_model_eval": (_i, [_i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p]),

@@ -42,13 +42,14 @@ __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout,
                                            int d, int s_e, int s_emit, const float (&q)[DP],
                                            const float (&p)[DP]) {
   const int two_d = 2 * d;
-  if (layout == PDEIP_TRAJ_TIME_SOA) {
-    float* o = base + (int64_t)s_e * two_d * n_total + n;
+  if (layout == PDEIP_TRAJ_TIME_SOA) {  // [2d][S_emit][N]: component planes, each plane time-major
+    float* o = base + (int64_t)s_e * n_total + n;
+    const int64_t plane = (int64_t)s_emit * n_total;
 #pragma unroll
     for (int i = 0; i < DP; ++i)
       if (i < d) {
-        __stcs(o + (int64_t)i * n_total, q[i]);
-        __stcs(o + (int64_t)(d + i) * n_total, p[i]);
+        __stcs(o + (int64_t)i * plane, q[i]);
+        __stcs(o + (int64_t)(d + i) * plane, p[i]);
       }
     return;
   }

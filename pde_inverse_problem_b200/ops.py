@@ -70,7 +70,7 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
     traj = None
     if want_traj:
         shape = {L.TRAJ_PARTICLE_MAJOR: (n, s_emit, two_d), L.TRAJ_TIME_MAJOR: (s_emit, n, two_d),
-                 L.TRAJ_TIME_SOA: (s_emit, two_d, n)}[traj_layout]
+                 L.TRAJ_TIME_SOA: (two_d, s_emit, n)}[traj_layout]
         if traj_out is not None:
             if traj_out.numel() < n * s_emit * two_d:
                 raise PdeipError("traj_out too small")
@@ -127,6 +127,34 @@ def gaussian_sample(n: int, dim: int, mu: Optional[torch.Tensor], cov_half: Opti
             "pdeip_gaussian_sample")
     launch_counter["n"] += 1
     return out
+
+
+def gaussian_sample_grouped(n_groups: int, per_group: int, dim: int, mus: torch.Tensor, cov_halves: torch.Tensor,
+                            seed: int, particle_offset: int = 0) -> torch.Tensor:
+    """[n_groups, per_group, dim] samples, one (mean, cov_half) per group."""
+    mus = _f32(mus, "mus")
+    cov_halves = _f32(cov_halves, "cov_halves")
+    if tuple(mus.shape) != (n_groups, dim) or tuple(cov_halves.shape) != (n_groups, dim, dim):
+        raise PdeipError("mus must be [G,dim] and cov_halves [G,dim,dim]")
+    out = torch.empty((n_groups, per_group, dim), device=mus.device, dtype=torch.float32)
+    L.check(L.load().pdeip_gaussian_sample_grouped(_ptr(out), n_groups, per_group, dim, _ptr(mus), _ptr(cov_halves),
+                                                   seed & 0xFFFFFFFFFFFFFFFF, particle_offset, _stream()),
+            "pdeip_gaussian_sample_grouped")
+    launch_counter["n"] += 1
+    return out
+
+
+def ou_exact_sample(n: int, U: torch.Tensor, s: torch.Tensor, B0: torch.Tensor, B: torch.Tensor, mt0: torch.Tensor,
+                    t_min: float, t_max: float, seed: int, particle_offset: int = 0, want_t: bool = False):
+    U, s, B0, B, mt0 = (_f32(t, nm) for t, nm in ((U, "U"), (s, "s"), (B0, "B0"), (B, "B"), (mt0, "mt0")))
+    d = s.numel()
+    out = torch.empty((n, d), device=U.device, dtype=torch.float32)
+    out_t = torch.empty((n,), device=U.device, dtype=torch.float32) if want_t else None
+    L.check(L.load().pdeip_ou_exact_sample(_ptr(out), _ptr(out_t), n, d, _ptr(U), _ptr(s), _ptr(B0), _ptr(B),
+                                           _ptr(mt0), float(t_min), float(t_max), seed & 0xFFFFFFFFFFFFFFFF,
+                                           particle_offset, _stream()), "pdeip_ou_exact_sample")
+    launch_counter["n"] += 1
+    return (out, out_t) if want_t else out
 
 
 # ------------------------------------------------------------------------------------------------

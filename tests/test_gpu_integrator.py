@@ -119,7 +119,7 @@ def test_full_trajectory_linear_drift_rtol_1e5(cuda, d):
         if layout == L.TRAJ_TIME_MAJOR:
             tr = tr.permute(1, 0, 2)
         elif layout == L.TRAJ_TIME_SOA:
-            tr = tr.permute(2, 0, 1)
+            tr = tr.permute(2, 1, 0)
         assert relmax(zl, last) < 1e-5
         assert relmax(tr, traj) < 1e-5
 
@@ -162,8 +162,8 @@ def test_emit_every_and_soa_state(cuda):
                                  noise=noise.float().to(cuda), tau0=tau0.float().to(cuda),
                                  state_layout=L.LAYOUT_SOA, traj_layout=L.TRAJ_TIME_SOA, emit_every=5, emit_offset=2)
     assert relmax(zl.t(), last) < 1e-5
-    assert tr.shape == (4, 2 * d, N)
-    assert relmax(tr.permute(2, 0, 1), traj[:, 2::5]) < 1e-5
+    assert tr.shape == (2 * d, 4, N)
+    assert relmax(tr.permute(2, 1, 0), traj[:, 2::5]) < 1e-5
 
 
 def test_philox_mode_equals_injected_device_noise(cuda):
