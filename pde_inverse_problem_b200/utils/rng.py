@@ -26,11 +26,13 @@ def PRNGKey(seed: int) -> int:
 
 def split(key: int, num: int = 2) -> List[int]:
     key = int(key) & _MASK
-    return [_splitmix64(key ^ _splitmix64(i + 1)) for i in range(num)]
+    base = _splitmix64(key ^ 0xA5A5A5A5A5A5A5A5)
+    return [_splitmix64((base + (i + 1) * 0xD1342543DE82EF95) & _MASK) for i in range(num)]
 
 
 def fold_in(key: int, data: int) -> int:
-    return _splitmix64((int(key) & _MASK) ^ _splitmix64(int(data) & _MASK))
+    base = _splitmix64((int(key) & _MASK) ^ 0x5A5A5A5A5A5A5A5A)
+    return _splitmix64((base + ((int(data) & _MASK) + 1) * 0x9FB21C651E98DF25) & _MASK)
 
 
 def randint(key: int, low: int, high: int) -> int:
