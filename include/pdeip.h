@@ -181,12 +181,15 @@ int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes, int set_k
 /* KMV pairwise set (kinetic_mckean_vlasov.py:20-97):  pairs (i,j,t), Delta = x[j,t] - x[i,t].
  * xv [n][nt][2d]; G [n][nt][d] = mean_i grad Phi(Delta_ij) (from pdeip_kmv_mean_grad; nullable -> skip the
  * |G|^2 gradient term); c [n][nt] = d_ss log rho + (d_s log rho)^2 + gamma d_s log rho. weight = 1/(n*n*nt). */
+size_t pdeip_kmv_workspace_bytes(int64_t n, int nt, int d);
+/* out_G [n][nt][d]; out_Gtrue (nullable) = mean_i grad Phi_true(Delta_ij) with Phi_true = D' A D / 2 (true_A [d][d]) */
 int pdeip_kmv_mean_grad(int model_kind, const float* params, int d, int hidden, int layers,
                         const float* xv, int64_t n, int nt, float* out_G, float* out_Gtrue,
-                        const float* true_A, void* stream);
+                        const float* true_A, void* workspace, size_t workspace_bytes, void* stream);
+/* accumulates the pair terms and, when G is given, mean|G|^2 + mean|G_true|^2 (loss) and mean|G_true - G|^2 */
 int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_bytes, int model_kind, const float* params,
                                   int d, int hidden, int layers, const float* xv, int64_t n, int nt,
-                                  const float* G, const float* c, float weight, void* stream);
+                                  const float* G, const float* G_true, const float* c, float weight, void* stream);
 
 /* loss assembly: loss = G2 - 2 D2 + 2 gamma_or_1 * D1 + GTRUE2 + BOUNDARY  (coefficients already folded in
  * by accumulate, see csrc/residual_common.cuh); sums/grad are device buffers. */

@@ -61,8 +61,9 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_residual_begin": (_i, [_p, _sz, _i, _i, _i, _i, _i, _p]),
     "pdeip_residual_accumulate": (_i, [_p, _sz, _i, _i, _p, _i, _i, _i, _i, _p, _l, _i, _f, _f, _i, _p, _i, _f,
                                        _i, _p]),
-    "pdeip_kmv_mean_grad": (_i, [_i, _p, _i, _i, _i, _p, _l, _i, _p, _p, _p, _p]),
-    "pdeip_residual_accumulate_kmv": (_i, [_p, _sz, _i, _p, _i, _i, _i, _p, _l, _i, _p, _p, _f, _p]),
+    "pdeip_kmv_workspace_bytes": (_sz, [_l, _i, _i]),
+    "pdeip_kmv_mean_grad": (_i, [_i, _p, _i, _i, _i, _p, _l, _i, _p, _p, _p, _p, _sz, _p]),
+    "pdeip_residual_accumulate_kmv": (_i, [_p, _sz, _i, _p, _i, _i, _i, _p, _l, _i, _p, _p, _p, _f, _p]),
     "pdeip_residual_finalize": (_i, [_p, _sz, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pdeip_adam_l2_step": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _i, _f, _p, _p]),
     "pdeip_moments_workspace_bytes": (_sz, [_i]),

@@ -40,8 +40,10 @@ int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& 
 int param_eval(int model_kind, const float* params, int d, int n_gaussian, const float* x, const float* v,
                float* out_value, float* out_grad, float* out_vHv, float* out_lap, int64_t n, cudaStream_t st);
 int kmv_mean_grad(int model_kind, const float* params, int d, int hidden, int layers, const float* xv, int64_t n,
-                  int nt, float* out_G, float* out_Gtrue, const float* true_A, cudaStream_t st);
-int kmv_residual_accumulate(int model_kind, const ResidualArgs& a, int hidden, cudaStream_t st);
+                  int nt, float* out_G, float* out_Gtrue, const float* true_A, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st);
+size_t kmv_ws_bytes(int64_t n, int nt, int d);
+int kmv_g_sums(const float* G, const float* Gtrue, int64_t n_rows, int d, float w, float* part_sums, cudaStream_t st);
 
 static int64_t num_params(int model_kind, int d, int hidden, int layers, int n_gaussian) {
   switch (model_kind) {
@@ -173,19 +175,24 @@ extern "C" int pdeip_model_eval(int model_kind, const float* params, int d, int 
   return param_eval(model_kind, params, d, n_gaussian, x, v, out_value, out_grad, out_vHv, out_lap, n, st);
 }
 
+extern "C" size_t pdeip_kmv_workspace_bytes(int64_t n, int nt, int d) {
+  if (n < 1 || nt < 1 || d < 1) return 0;
+  return kmv_ws_bytes(n, nt, d);
+}
+
 extern "C" int pdeip_kmv_mean_grad(int model_kind, const float* params, int d, int hidden, int layers,
                                    const float* xv, int64_t n, int nt, float* out_G, float* out_Gtrue,
-                                   const float* true_A, void* stream) {
+                                   const float* true_A, void* workspace, size_t workspace_bytes, void* stream) {
   PDEIP_REQUIRE(params && xv && out_G, PDEIP_ERR_INVALID_ARG, "NULL argument");
   PDEIP_REQUIRE(n >= 1 && nt >= 1, PDEIP_ERR_INVALID_ARG, "n / nt must be >= 1");
-  return kmv_mean_grad(model_kind, params, d, hidden, layers, xv, n, nt, out_G, out_Gtrue, true_A,
-                       (cudaStream_t)stream);
+  return kmv_mean_grad(model_kind, params, d, hidden, layers, xv, n, nt, out_G, out_Gtrue, true_A, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_bytes, int model_kind,
                                              const float* params, int d, int hidden, int layers, const float* xv,
-                                             int64_t n, int nt, const float* G, const float* c, float weight,
-                                             void* stream) {
+                                             int64_t n, int nt, const float* G, const float* G_true,
+                                             const float* c, float weight, void* stream) {
   const int64_t P = num_params(model_kind, d, hidden, layers, 0);
   PDEIP_REQUIRE(P > 0, PDEIP_ERR_INVALID_ARG, "unknown model kind %d", model_kind);
   PDEIP_REQUIRE(workspace != nullptr && workspace_bytes >= residual_ws_bytes(P), PDEIP_ERR_WORKSPACE,
@@ -197,5 +204,11 @@ extern "C" int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_b
   a.params = params; a.points = xv; a.n_points = n * n * nt; a.layout = PDEIP_LAYOUT_AOS; a.d = d;
   a.layers = layers; a.weight = weight; a.G = G; a.c = c; a.kmv_n = n; a.kmv_nt = nt;
   a.ws = (float*)workspace; a.pstride = residual_pstride(P);
-  return kmv_residual_accumulate(model_kind, a, hidden, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (G) {  // |G|^2, |G_true|^2, |G_true - G|^2 with weight 1/(n*nt) = weight * n
+    int rc = kmv_g_sums(G, G_true, n * nt, d, weight * (float)n, a.ws + P, st);
+    if (rc != PDEIP_OK) return rc;
+  }
+  if (model_kind == PDEIP_MODEL_MLP) return mlp_residual_accumulate_fp32(PDEIP_SET_KMV_PAIRS, a, hidden, st);
+  return param_residual_accumulate(PDEIP_SET_KMV_PAIRS, model_kind, a, 0, st);
 }

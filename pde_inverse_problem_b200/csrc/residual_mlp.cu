@@ -73,9 +73,29 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp_residual_kernel(const Residual
     const bool valid = p < a.n_points;
     const float wt = valid ? a.weight : 0.f;
     float v[kDMax];
-    for (int i = 0; i < d; ++i) {
-      st.x[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, dim)] : 0.f;
-      if (kinetic) v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, dim)] : 0.f;
+    float kmv_u[kDMax];
+    float kmv_kappa = 0.f;
+    if (SET == PDEIP_SET_KMV_PAIRS) {
+      // pair index p -> (i, j, t): Delta = x[j,t] - x[i,t], v = v[j,t], u = G[j,t], kappa = 2 c[j,t]  (:23,:46-48)
+      const int64_t n = a.kmv_n;
+      const int nt = a.kmv_nt;
+      const int64_t pp = valid ? p : 0;
+      const int t = (int)(pp % nt);
+      const int64_t ij = pp / nt;
+      const int64_t j = ij % n, i = ij / n;
+      const float* rj = a.points + (j * nt + t) * 2 * d;
+      const float* ri = a.points + (i * nt + t) * 2 * d;
+      for (int c = 0; c < d; ++c) {
+        st.x[c] = valid ? rj[c] - ri[c] : 0.f;
+        v[c] = valid ? rj[d + c] : 0.f;
+        kmv_u[c] = (valid && a.G) ? a.G[(j * nt + t) * d + c] : 0.f;
+      }
+      kmv_kappa = valid ? 2.f * a.c[j * nt + t] * wt : 0.f;
+    } else {
+      for (int i = 0; i < d; ++i) {
+        st.x[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, dim)] : 0.f;
+        if (kinetic) v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, dim)] : 0.f;
+      }
     }
     net.reset_adjoints();
     net.primal_forward();
@@ -131,6 +151,20 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp_residual_kernel(const Residual
       net.primal_reverse(ws, 0.f);
       sums[PDEIP_SUM_BOUNDARY] += wt * a.coef * D1;
       sums[PDEIP_SUM_LOSS] += wt * a.coef * D1;
+    } else if (SET == PDEIP_SET_KMV_PAIRS) {
+      const float V = net.value();
+      float D1, D2;
+      net.template direction_forward<true>(v, u1, u2, D1, D2);
+      net.template direction_reverse<true>(ws, v, -2.f * wt, 0.f, u1, u2);
+      if (a.G) {  // d|G_j|^2 through the constant direction u = G_j
+        float d1g, d2g;
+        net.template direction_forward<false>(kmv_u, u1, u2, d1g, d2g);
+        net.template direction_reverse<false>(ws, kmv_u, 0.f, 2.f * wt, u1, u2);
+      }
+      net.primal_reverse(ws, kmv_kappa);
+      sums[PDEIP_SUM_D2] += wt * D2;
+      sums[PDEIP_SUM_D1] += 0.5f * kmv_kappa * V;
+      sums[PDEIP_SUM_LOSS] += -2.f * wt * D2 + kmv_kappa * V;
     } else {  // FP boundary
       const float V = net.value();
       net.primal_reverse(ws, a.coef * wt);
@@ -183,6 +217,7 @@ static int launch_mlp_residual(int set_kind, const ResidualArgs& a, cudaStream_t
     case PDEIP_SET_KFP_BOUNDARY: LAUNCH_SET(PDEIP_SET_KFP_BOUNDARY); break;
     case PDEIP_SET_FP_0T: LAUNCH_SET(PDEIP_SET_FP_0T); break;
     case PDEIP_SET_FP_BOUNDARY: LAUNCH_SET(PDEIP_SET_FP_BOUNDARY); break;
+    case PDEIP_SET_KMV_PAIRS: LAUNCH_SET(PDEIP_SET_KMV_PAIRS); break;
     default: PDEIP_REQUIRE(false, PDEIP_ERR_INVALID_ARG, "unknown point-set kind %d", set_kind);
   }
 #undef LAUNCH_SET

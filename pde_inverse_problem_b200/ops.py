@@ -335,3 +335,43 @@ def gather_0T(dataset: torch.Tensor, sample_index: torch.Tensor, interval: int, 
                                      interval, shift, n_time_sel, _ptr(out), _stream()), "pdeip_gather_0T")
     launch_counter["n"] += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# KMV pairwise residual (kinetic_mckean_vlasov.py:11-120)
+# ------------------------------------------------------------------------------------------------
+def kmv_mean_grad(spec: ModelSpec, params: torch.Tensor, xv: torch.Tensor, true_A: Optional[torch.Tensor] = None):
+    """G[j,t] = mean_i grad Phi(x[j,t] - x[i,t]) and, if true_A is given, the same for Phi_true = D'AD/2.
+    xv: [n, nt, 2d]."""
+    params = _f32(params, "params")
+    xv = _f32(xv, "xv")
+    true_A = _f32(true_A, "true_A", allow_none=True)
+    n, nt, two_d = xv.shape
+    d = two_d // 2
+    lib = L.load()
+    ws_bytes = int(lib.pdeip_kmv_workspace_bytes(n, nt, d))
+    ws = torch.empty((ws_bytes // 4,), device=xv.device, dtype=torch.float32)
+    G = torch.empty((n, nt, d), device=xv.device, dtype=torch.float32)
+    Gt = torch.empty_like(G) if true_A is not None else None
+    L.check(lib.pdeip_kmv_mean_grad(spec.kind, _ptr(params), d, spec.hidden, spec.layers, _ptr(xv), n, nt, _ptr(G),
+                                    _ptr(Gt), _ptr(true_A), _ptr(ws), ws_bytes, _stream()), "pdeip_kmv_mean_grad")
+    launch_counter["n"] += 2
+    return G, Gt
+
+
+def kmv_value_and_grad(model, params, flat: torch.Tensor, xv: torch.Tensor, c: torch.Tensor, true_A: torch.Tensor,
+                       acc: "ResidualAccumulator", result_dict):
+    """Phase 1 (mean gradient per sample), then the pair set with the extra direction G_j and kappa = 2 c_j."""
+    xv = _f32(xv, "xv")
+    c = _f32(c, "c")
+    n, nt, _ = xv.shape
+    spec = model.spec
+    G, Gt = kmv_mean_grad(spec, flat, xv, true_A)
+    acc.begin()
+    L.check(L.load().pdeip_residual_accumulate_kmv(_ptr(acc.ws), acc.ws_bytes, spec.kind, _ptr(flat), spec.d,
+                                                   spec.hidden, spec.layers, _ptr(xv), n, nt, _ptr(G), _ptr(Gt),
+                                                   _ptr(c), 1.0 / (float(n) * n * nt), _stream()),
+            "pdeip_residual_accumulate_kmv")
+    launch_counter["n"] += 2
+    sums, grad = acc.finalize()
+    return result_dict(model, params, sums, grad)
