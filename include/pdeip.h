@@ -223,6 +223,16 @@ int pdeip_ensemble_moments(const float* z, int64_t n, int dim, int layout, float
 int pdeip_gather_0T(const float* dataset, int64_t n_traj, int n_time, int dim, const int64_t* sample_index,
                     int64_t n_sel, int interval, int shift, int n_time_sel, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * self-test of the tcgen05 building blocks (one 128 x N x K bf16 GEMM through the helpers of csrc/umma.cuh);
+ * mode 0: D = A B^T (K-major A [128][K], B [N][K]); 1: D = A B (B [K][N], transposed view); 2: D = A^T B
+ * (A [K][128], B [K][N], both transposed views); 3: TMEM st/ld round trip.  status (device int) != 0 on timeout.
+ * ------------------------------------------------------------------------------------------- */
+/* 0 = every tcgen05 phase of the PDEIP_PATH_TENSOR launches so far completed; 1 = a bounded mbarrier wait timed
+ * out (results invalid).  Synchronises the stream. */
+int pdeip_tensor_path_status(void* stream, int* out_status);
+int pdeip_debug_umma(int mode, const float* A, const float* B, float* D, int K, int N, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

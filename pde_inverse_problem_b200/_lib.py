@@ -68,6 +68,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_adam_l2_step": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _i, _f, _p, _p]),
     "pdeip_moments_workspace_bytes": (_sz, [_i]),
     "pdeip_ensemble_moments": (_i, [_p, _l, _i, _i, _p, _p, _sz, _p]),
+    "pdeip_tensor_path_status": (_i, [_p, _p]),
+    "pdeip_debug_umma": (_i, [_i, _p, _p, _p, _i, _i, _p, _p]),
     "pdeip_gather_0T": (_i, [_p, _l, _i, _i, _p, _l, _i, _i, _i, _p, _p]),
 }
 

@@ -1,0 +1,98 @@
+// umma_selftest.cu — single-tile tcgen05 GEMMs through the helpers of umma.cuh, for unit tests of the
+// descriptor / core-matrix-layout conventions (K-major, MN-major "transposed view", TMEM ld/st).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pdeip {
+
+// mode 0: D[m][n] = sum_k A[m][k] * B[n][k]      A [128][K], B [N][K]        (both K-major)
+// mode 1: D[m][n] = sum_k A[m][k] * B[k][n]      A [128][K], B [K][N]        (B transposed view)
+// mode 2: D[m][n] = sum_r A[r][m] * B[r][n]      A [K][128], B [K][N]        (both transposed views)
+// mode 3: TMEM st/ld round trip: D[m][n] = A[m][n] (K = N)
+__global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
+                                                            const float* __restrict__ B, float* __restrict__ D,
+                                                            int K, int N, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a_rows = (mode == 2) ? K : 128, a_cols = (mode == 2) ? 128 : K;
+  const int b_rows = (mode == 0) ? N : K, b_cols = (mode == 0) ? K : N;
+  const uint32_t a_rg = (uint32_t)(a_cols / 8) * 128u, b_rg = (uint32_t)(b_cols / 8) * 128u;
+  uint8_t* a_tile = sm;
+  uint8_t* b_tile = sm + (size_t)(a_rows / 8) * a_rg;
+  if (warp == 0) {
+    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 64);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_u32(&mbar), 1);
+    umma::fence_mbar_init();
+  }
+  if (mode != 3) {
+    for (int idx = tid; idx < a_rows * (a_cols / 8); idx += 128) {
+      const int r = idx / (a_cols / 8), cg = idx % (a_cols / 8);
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = A[r * a_cols + cg * 8 + i];
+      umma::store_chunk(a_tile, umma::chunk_off(r, cg, a_rg), v);
+    }
+    for (int idx = tid; idx < b_rows * (b_cols / 8); idx += 128) {
+      const int r = idx / (b_cols / 8), cg = idx % (b_cols / 8);
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = B[r * b_cols + cg * 8 + i];
+      umma::store_chunk(b_tile, umma::chunk_off(r, cg, b_rg), v);
+    }
+  }
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+  bool ok = true;
+  if (mode == 3) {
+    for (int c = 0; c < N; c += 8) {
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = A[tid * N + c + i];
+      umma::tmem_st8(lane_addr + c, v);
+    }
+  } else {
+    if (tid == 0) {
+      const uint32_t at = umma::smem_u32(a_tile), bt = umma::smem_u32(b_tile);
+      if (mode == 0) umma::gemm_kk(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
+      else if (mode == 1) umma::gemm_km(tbase, at, a_rg, 0, bt, b_rg, 0, 0, K, N, 0);
+      else umma::gemm_mm(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
+      umma::commit(umma::smem_u32(&mbar));
+    }
+    ok = umma::mbar_wait(umma::smem_u32(&mbar), 0);
+    umma::fence_after_sync();
+  }
+  if (ok) {
+    for (int c = 0; c < N; c += 8) {
+      float v[8];
+      umma::tmem_ld8(lane_addr + c, v);
+      for (int i = 0; i < 8; ++i) D[tid * N + c + i] = v[i];
+    }
+  } else if (tid == 0) {
+    *status = 1;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 64);
+}
+
+}  // namespace pdeip
+
+using namespace pdeip;
+
+extern "C" int pdeip_debug_umma(int mode, const float* A, const float* B, float* D, int K, int N, int* status,
+                                void* stream) {
+  PDEIP_REQUIRE(mode >= 0 && mode <= 3 && A && D && status, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  PDEIP_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 64, PDEIP_ERR_INVALID_ARG,
+                "K must be a multiple of 16 in [16,128], N a multiple of 16 in [16,64]");
+  const size_t smem = (size_t)128 * 128 * 2 + (size_t)128 * 64 * 2 + 1024;
+  PDEIP_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, A, B, D, K, N, status);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}

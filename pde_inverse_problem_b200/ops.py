@@ -375,3 +375,11 @@ def kmv_value_and_grad(model, params, flat: torch.Tensor, xv: torch.Tensor, c: t
     launch_counter["n"] += 2
     sums, grad = acc.finalize()
     return result_dict(model, params, sums, grad)
+
+
+def tensor_path_status() -> int:
+    """0 if every tcgen05 phase of the tensor-path launches so far completed (synchronises the stream)."""
+    import ctypes as C
+    out = C.c_int(-1)
+    L.check(L.load().pdeip_tensor_path_status(_stream(), C.addressof(out)), "pdeip_tensor_path_status")
+    return int(out.value)

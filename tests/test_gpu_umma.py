@@ -1,0 +1,40 @@
+"""GPU: tcgen05 building blocks (descriptor / core-matrix layout conventions of csrc/umma.cuh)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, A, B, K, N, cuda):
+    from pde_inverse_problem_b200 import _lib as L
+    lib = L.load()
+    D = torch.full((128, N), float("nan"), device=cuda)
+    status = torch.zeros(1, dtype=torch.int32, device=cuda)
+    st = lib.pdeip_debug_umma(mode, A.data_ptr(), B.data_ptr() if B is not None else None, D.data_ptr(), K, N,
+                              status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    L.check(st, "pdeip_debug_umma")
+    torch.cuda.synchronize()
+    assert status.item() == 0, "tcgen05 self-test timed out"
+    return D
+
+
+@pytest.mark.parametrize("K,N", [(16, 16), (32, 32), (48, 32), (32, 48), (128, 48)])
+def test_umma_layout_conventions(cuda, K, N):
+    g = torch.Generator().manual_seed(K * 100 + N)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    A = bf(torch.randn(128, K, generator=g)).to(cuda)
+    B0 = bf(torch.randn(N, K, generator=g)).to(cuda)
+    D = _run(0, A, B0, K, N, cuda)
+    assert torch.allclose(D, A @ B0.T, rtol=1e-4, atol=1e-4), "K-major x K-major"
+    B1 = bf(torch.randn(K, N, generator=g)).to(cuda)
+    D = _run(1, A, B1, K, N, cuda)
+    assert torch.allclose(D, A @ B1, rtol=1e-4, atol=1e-4), "K-major x transposed view"
+    A2 = bf(torch.randn(K, 128, generator=g)).to(cuda)
+    D = _run(2, A2, B1, K, N, cuda)
+    assert torch.allclose(D, A2.T @ B1, rtol=1e-4, atol=1e-4), "transposed view x transposed view"
+
+
+def test_tmem_store_load_roundtrip(cuda):
+    A = torch.randn(128, 32, device=cuda)
+    D = _run(3, A, None, 32, 32, cuda)
+    assert torch.equal(D, A)
