@@ -56,6 +56,22 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// exactly one lane of a converged warp (the compiler then issues tcgen05.mma / commit without a per-lane
+// "waterfall" loop, which a plain `lane == 0` test provokes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void commit(uint32_t mbar_saddr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_saddr)
                : "memory");
@@ -187,6 +203,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
       "tcgen05.wait::st.sync.aligned;\n" ::"r"(taddr),
       "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
       "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};\n\t"
+      "tcgen05.wait::st.sync.aligned;\n" ::"r"(taddr),
+      "r"(__float_as_uint(a)), "r"(__float_as_uint(b))
       : "memory");
 }
 
