@@ -178,10 +178,10 @@ def run_ours(args):
             e[0].record()
             z_last, traj, _ = ops.kl_integrate(z0[lo:hi], S, dt, cfg.gamma, drift_kind, drift, n_gaussian=K,
                                                seed=seed, particle_offset=offset + lo, traj_layout=L.TRAJ_TIME_SOA,
-                                               traj_out=hp.traj, z_last_out=hp.z_last[:nc])
+                                               traj_out=hp.traj, z_last_out=hp.z_last[:nc], emit_drift=True)
             e[1].record()
-            hp.acc.accumulate(L.SET_KFP_0T, flat, traj.view(2 * d, hp.s_emit * nc), 1.0 / (n_global * hp.s_emit),
-                              coef=cfg.gamma, layout=L.LAYOUT_SOA, true_grad=true, path=path)
+            hp.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * d, hp.s_emit * nc), 1.0 / (n_global * hp.s_emit),
+                              coef=cfg.gamma, layout=L.LAYOUT_SOA, true_grad=hp.true_in_points, path=path)
             e[2].record()
             ev.append(e)
         hp.acc.finalize()
@@ -249,7 +249,7 @@ def run_ours(args):
         res_rate = n * hp.s_emit / t_res  # per GPU
         res_tflops = res_rate * flop_eval / 1e12
         int_rate = n * (S + 1) / t_int
-        int_gbs = n * hp.s_emit * 2 * d * 4 / t_int / 1e9
+        int_gbs = n * hp.s_emit * 3 * d * 4 / t_int / 1e9  # [x, v, grad U(x)] per emitted sample
         line = {
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": shard.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -273,7 +273,7 @@ def run_ours(args):
             "kernels": {
                 "kl_integrate": {"bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": int_gbs / pk["hbm"], "particle_steps_per_s_per_gpu": int_rate,
-                                 "bytes_per_emitted_step": 2 * d * 4, "ms_per_step": t_int * 1e3},
+                                 "bytes_per_emitted_step": 3 * d * 4, "ms_per_step": t_int * 1e3},
                 "mlp_residual": {"ms_per_step": t_res * 1e3, "evals_per_s_per_gpu": res_rate},
             },
         }

@@ -51,6 +51,7 @@ extern "C" {
 #define PDEIP_DRIFT_LINEAR    1 /* grad U = A x          A row-major [d][d]  (kinetic OU, README.md:64-71) */
 #define PDEIP_DRIFT_GMM       2 /* core/potential.py:32-61, params = mus [K][d] */
 #define PDEIP_DRIFT_MEANFIELD 3 /* grad U = A (x - xbar), params = [A (d*d), xbar (d)] */
+#define PDEIP_DRIFT_IN_POINTS 4 /* residual kernels only: grad V_true is stored after each point's own components */
 
 /* step schedules */
 #define PDEIP_SCHEDULE_REFERENCE 0 /* step(tau0), (S-1) x step(dt), step(dt - tau0): sampling_utils.py:32-46 */
@@ -98,6 +99,8 @@ int pdeip_sm_count(void);
  * (sampling_utils.py:48).  noise: NULL -> in-register Philox4x32-10 keyed by (seed, particle_offset
  * + n, step_offset + s); else injected normals [N][S+1][d] (REFERENCE schedule) / [N][S][d] (UNIFORM).
  * tau0: NULL -> Philox uniform [0,1)*dt; else injected [N] (REFERENCE schedule only).
+ * emit_drift != 0: every emitted sample is [x, v, grad U(x)] (3d floats; the integrator evaluates grad U(x) anyway at
+ * the following step), which the residual kernels accept as grad V_true via PDEIP_DRIFT_IN_POINTS.
  * ------------------------------------------------------------------------------------------- */
 int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
                        int64_t n_particles, int d, int n_steps, float dt, float gamma,
@@ -105,7 +108,7 @@ int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
                        const float* noise, const float* tau0,
                        uint64_t seed, uint64_t particle_offset, uint32_t step_offset,
                        int schedule, int state_layout, int traj_layout,
-                       int emit_every, int emit_offset, void* stream);
+                       int emit_every, int emit_offset, int emit_drift, void* stream);
 
 /* the normals / uniforms pdeip_kl_integrate draws in Philox mode (for parity tests):
  * normals [N][n_draws][d] for steps step_offset..step_offset+n_draws-1; uniforms [N] (tau0/dt). */
@@ -170,7 +173,8 @@ int pdeip_residual_begin(void* workspace, size_t workspace_bytes, int model_kind
  * weight multiplies every per-point contribution (use 1 / global point count).
  * coef: KFP_0T -> gamma_friction;  *_BOUNDARY -> +-2/T;  FP_0T, KMV -> unused.
  * true_kind/true_params/true_n_gaussian/true_sigma: drift spec (PDEIP_DRIFT_LINEAR / _GMM / _NONE) of
- *   grad V_true, used by the *_0T kinds for sum|gV_true|^2 and "loss ground truth".
+ *   grad V_true, used by the *_0T kinds for sum|gV_true|^2 and "loss ground truth"; PDEIP_DRIFT_IN_POINTS: the points
+ *   carry d extra components holding grad V_true (rows of dim + d floats / dim + d planes).
  * path: PDEIP_PATH_FP32 or PDEIP_PATH_TENSOR (MLP model, KFP kinds only). */
 int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes, int set_kind, int model_kind,
                               const float* params, int d, int hidden, int layers, int n_gaussian,

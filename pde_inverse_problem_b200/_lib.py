@@ -24,7 +24,7 @@ class PdeipError(RuntimeError):
 OK = 0
 LAYOUT_AOS, LAYOUT_SOA = 0, 2
 TRAJ_PARTICLE_MAJOR, TRAJ_TIME_MAJOR, TRAJ_TIME_SOA = 0, 1, 2
-DRIFT_NONE, DRIFT_LINEAR, DRIFT_GMM, DRIFT_MEANFIELD = 0, 1, 2, 3
+DRIFT_NONE, DRIFT_LINEAR, DRIFT_GMM, DRIFT_MEANFIELD, DRIFT_IN_POINTS = 0, 1, 2, 3, 4
 SCHEDULE_REFERENCE, SCHEDULE_UNIFORM = 0, 1
 MODEL_MLP, MODEL_GMM, MODEL_QUADRATIC = 0, 1, 2
 SET_KFP_0T, SET_KFP_BOUNDARY, SET_FP_0T, SET_FP_BOUNDARY, SET_KMV_PAIRS = 0, 1, 2, 3, 4
@@ -46,7 +46,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_last_error": (C.c_char_p, []),
     "pdeip_sm_count": (_i, []),
     "pdeip_kl_integrate": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _f, _i, _p, _i, _f, _p, _p, _u64, _u64, _u32,
-                                _i, _i, _i, _i, _i, _p]),
+                                _i, _i, _i, _i, _i, _i, _p]),
     "pdeip_philox_normals": (_i, [_p, _l, _i, _i, _u64, _u64, _u32, _p]),
     "pdeip_philox_uniforms": (_i, [_p, _l, _u64, _u64, _p]),
     "pdeip_philox_raw": (_i, [_p, _p, _p, _l, _p]),

@@ -123,10 +123,11 @@ extern "C" int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes
   PDEIP_REQUIRE(n_points >= 0, PDEIP_ERR_INVALID_ARG, "n_points < 0");
   PDEIP_REQUIRE(layout == PDEIP_LAYOUT_AOS || layout == PDEIP_LAYOUT_SOA, PDEIP_ERR_INVALID_ARG, "bad layout %d",
                 layout);
-  PDEIP_REQUIRE(true_kind == PDEIP_DRIFT_NONE || true_kind == PDEIP_DRIFT_LINEAR || true_kind == PDEIP_DRIFT_GMM,
-                PDEIP_ERR_INVALID_ARG, "true_kind must be NONE, LINEAR or GMM");
-  PDEIP_REQUIRE(true_kind == PDEIP_DRIFT_NONE || true_params != nullptr, PDEIP_ERR_INVALID_ARG,
-                "true_params is NULL");
+  PDEIP_REQUIRE(true_kind == PDEIP_DRIFT_NONE || true_kind == PDEIP_DRIFT_LINEAR || true_kind == PDEIP_DRIFT_GMM ||
+                    true_kind == PDEIP_DRIFT_IN_POINTS,
+                PDEIP_ERR_INVALID_ARG, "true_kind must be NONE, LINEAR, GMM or IN_POINTS");
+  PDEIP_REQUIRE(true_kind == PDEIP_DRIFT_NONE || true_kind == PDEIP_DRIFT_IN_POINTS || true_params != nullptr,
+                PDEIP_ERR_INVALID_ARG, "true_params is NULL");
   if (n_points == 0) return PDEIP_OK;
   PDEIP_REQUIRE(points != nullptr, PDEIP_ERR_INVALID_ARG, "points is NULL");
   ResidualArgs a;

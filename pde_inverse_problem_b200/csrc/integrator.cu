@@ -35,13 +35,13 @@ struct IntegrateArgs {
   int emit_every;
   int emit_offset;
   int s_emit;  // number of emitted samples
+  int emit_drift;  // 1: every emitted sample carries grad U(x) as components [2d, 3d)
 };
 
 template <int DP>
 __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
-                                           int d, int s_e, int s_emit, const float (&q)[DP],
+                                           int d, int C, int s_e, int s_emit, const float (&q)[DP],
                                            const float (&p)[DP]) {
-  const int two_d = 2 * d;
   if (layout == PDEIP_TRAJ_TIME_SOA) {  // [2d][S_emit][N]: component planes, each plane time-major
     float* o = base + (int64_t)s_e * n_total + n;
     const int64_t plane = (int64_t)s_emit * n_total;
@@ -53,8 +53,8 @@ __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout,
       }
     return;
   }
-  float* o = (layout == PDEIP_TRAJ_PARTICLE_MAJOR) ? base + (n * s_emit + s_e) * two_d
-                                                    : base + ((int64_t)s_e * n_total + n) * two_d;
+  float* o = (layout == PDEIP_TRAJ_PARTICLE_MAJOR) ? base + (n * s_emit + s_e) * C
+                                                    : base + ((int64_t)s_e * n_total + n) * C;
   if (DP % 4 == 0 && d == DP) {
 #pragma unroll
     for (int i4 = 0; i4 < DP / 4; ++i4) {
@@ -69,6 +69,31 @@ __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout,
         o[i] = q[i];
         o[d + i] = p[i];
       }
+  }
+}
+
+// grad U(x) of sample s_e -> components [2d, 3d) of its slot (row width C = 3d)
+template <int DP>
+__device__ __forceinline__ void emit_drift_vals(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
+                                                int d, int C, int s_e, int s_emit, const float (&g)[DP]) {
+  if (layout == PDEIP_TRAJ_TIME_SOA) {
+    float* o = base + (int64_t)s_e * n_total + n;
+    const int64_t plane = (int64_t)s_emit * n_total;
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) __stcs(o + (int64_t)(2 * d + i) * plane, g[i]);
+    return;
+  }
+  float* o = (layout == PDEIP_TRAJ_PARTICLE_MAJOR) ? base + (n * s_emit + s_e) * C + 2 * d
+                                                    : base + ((int64_t)s_e * n_total + n) * C + 2 * d;
+  if (DP % 4 == 0 && d == DP) {
+#pragma unroll
+    for (int i4 = 0; i4 < DP / 4; ++i4)
+      __stcs(reinterpret_cast<float4*>(o) + i4, make_float4(g[4 * i4], g[4 * i4 + 1], g[4 * i4 + 2], g[4 * i4 + 3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) o[i] = g[i];
   }
 }
 
@@ -111,6 +136,7 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
   }
   const int total_steps = ref_sched ? a.n_steps + 1 : a.n_steps;
   const int n_draws = total_steps;
+  const int C = a.emit_drift ? 3 * d : 2 * d;  // floats per emitted sample
 
   for (int s = 0; s < total_steps; ++s) {
     float h = a.dt;
@@ -128,6 +154,9 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
 #pragma unroll
       for (int i = 0; i < DP; ++i) g[i] = 0.0f;
     }
+    // the drift just evaluated is grad U at the state emitted as sample s-1
+    if (a.emit_drift && a.traj && s >= 1 && ((s - 1) % a.emit_every) == a.emit_offset)
+      emit_drift_vals<DP>(a.traj, a.traj_layout, n, a.n, d, C, (s - 1) / a.emit_every, a.s_emit, g);
     // noise
     float xi[DP];
     if (a.noise) {
@@ -156,8 +185,21 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
     // UNIFORM schedule emits every state.
     const bool is_sample = ref_sched ? (s < a.n_steps) : true;
     if (a.traj && is_sample && (s % a.emit_every) == a.emit_offset) {
-      emit_state<DP>(a.traj, a.traj_layout, n, a.n, d, s / a.emit_every, a.s_emit, q, p);
+      emit_state<DP>(a.traj, a.traj_layout, n, a.n, d, C, s / a.emit_every, a.s_emit, q, p);
     }
+  }
+  if (a.emit_drift && a.traj && !ref_sched && ((total_steps - 1) % a.emit_every) == a.emit_offset) {
+    // UNIFORM schedule: the last emitted sample has no following step; evaluate its drift once more
+    float g[DP];
+    if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
+      gmm_grad_thread<DP>(q, smem, a.n_gaussian, a.inv_sigma2, g);
+    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+      linear_grad_thread<DP>(q, A_s, shift_s, g);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DP; ++i) g[i] = 0.0f;
+    }
+    emit_drift_vals<DP>(a.traj, a.traj_layout, n, a.n, d, C, (total_steps - 1) / a.emit_every, a.s_emit, g);
   }
   if (a.z_last) {
 #pragma unroll
@@ -264,7 +306,7 @@ extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, f
                                   const float* noise, const float* tau0, uint64_t seed,
                                   uint64_t particle_offset, uint32_t step_offset, int schedule,
                                   int state_layout, int traj_layout, int emit_every, int emit_offset,
-                                  void* stream) {
+                                  int emit_drift, void* stream) {
   PDEIP_REQUIRE(z0 != nullptr, PDEIP_ERR_INVALID_ARG, "z0 is NULL");
   PDEIP_REQUIRE(n_particles >= 0 && d >= 1 && d <= 32, PDEIP_ERR_UNSUPPORTED,
                 "integrator supports 1 <= d <= 32 (got d=%d)", d);
@@ -289,6 +331,7 @@ extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, f
   a.noise = noise; a.tau0 = tau0; a.seed = seed; a.particle_offset = particle_offset;
   a.step_offset = step_offset; a.schedule = schedule; a.state_layout = state_layout;
   a.traj_layout = traj_layout; a.emit_every = emit_every; a.emit_offset = emit_offset;
+  a.emit_drift = emit_drift ? 1 : 0;
   const int n_samples = n_steps;  // both schedules expose n_steps samples
   a.s_emit = (n_samples - emit_offset + emit_every - 1) / emit_every;
   cudaStream_t st = (cudaStream_t)stream;

@@ -148,9 +148,10 @@ __global__ void __launch_bounds__(kPNW * 32, 1) gmm_param_residual_kernel(const 
     const bool valid = p < a.n_points;
     const float wt = valid ? a.weight : 0.f;
     float y[kPD], v[kPD];
+    const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);
     for (int i = 0; i < d; ++i) {
-      y[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, 2 * d)] : 0.f;
-      v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, 2 * d)] : 0.f;
+      y[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, dimw)] : 0.f;
+      v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, dimw)] : 0.f;
     }
     gmm_point_forward(mus_s, K, d, y, v, pt);
     float alpha, beta, cg;
@@ -158,7 +159,11 @@ __global__ void __launch_bounds__(kPNW * 32, 1) gmm_param_residual_kernel(const 
       const float gamma = a.coef;
       alpha = -2.f * wt; beta = 2.f * gamma * wt; cg = wt;
       float gt[kPD];
-      true_grad_thread(a.tg, tp, d, y, gt);
+      if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+        for (int i = 0; i < d; ++i) gt[i] = valid ? a.points[elem_index(a.layout, p, 2 * d + i, a.n_points, dimw)] : 0.f;
+      } else {
+        true_grad_thread(a.tg, tp, d, y, gt);
+      }
       float g2 = 0.f, gt2 = 0.f, gd2 = 0.f;
       for (int i = 0; i < d; ++i) {
         g2 = fmaf(pt.g[i], pt.g[i], g2);
@@ -287,6 +292,7 @@ __global__ void __launch_bounds__(kPNW * 32, 1) quad_param_residual_kernel(const
     const bool valid = p < a.n_points;
     const float wt = valid ? a.weight : 0.f;
     float y[kPD], v[kPD], u[kPD], g[kPD];
+    const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);
     float alpha = 0.f, beta = 0.f, beta2 = 0.f, kappa = 0.f, cg = 0.f;
     if (SET == PDEIP_SET_KMV_PAIRS) {
       // pair index p -> (i, j, t): Delta = x[j,t] - x[i,t], v = v[j,t], u = G[j,t], kappa = 2 c[j,t]
@@ -308,8 +314,8 @@ __global__ void __launch_bounds__(kPNW * 32, 1) quad_param_residual_kernel(const
       kappa = valid ? 2.f * a.c[j * nt + t] * wt : 0.f;
     } else {
       for (int i = 0; i < d; ++i) {
-        y[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, 2 * d)] : 0.f;
-        v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, 2 * d)] : 0.f;
+        y[i] = valid ? a.points[elem_index(a.layout, p, i, a.n_points, dimw)] : 0.f;
+        v[i] = valid ? a.points[elem_index(a.layout, p, d + i, a.n_points, dimw)] : 0.f;
         u[i] = 0.f;
       }
     }
@@ -319,7 +325,11 @@ __global__ void __launch_bounds__(kPNW * 32, 1) quad_param_residual_kernel(const
       const float gamma = a.coef;
       alpha = -2.f * wt; beta = 2.f * gamma * wt; cg = wt;
       float gt[kPD];
-      true_grad_thread(a.tg, tp, d, y, gt);
+      if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+        for (int i = 0; i < d; ++i) gt[i] = valid ? a.points[elem_index(a.layout, p, 2 * d + i, a.n_points, dimw)] : 0.f;
+      } else {
+        true_grad_thread(a.tg, tp, d, y, gt);
+      }
       float g2 = 0.f, gt2 = 0.f, gd2 = 0.f;
       for (int i = 0; i < d; ++i) {
         g2 = fmaf(g[i], g[i], g2);

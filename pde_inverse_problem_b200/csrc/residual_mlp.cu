@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp_residual_kernel(const Residual
   PointState<H, LHMAX> st;
   MlpThread<H, LHMAX> net(sh, sp, st);
   constexpr bool kinetic = (SET == PDEIP_SET_KFP_0T || SET == PDEIP_SET_KFP_BOUNDARY);
-  const int dim = kinetic ? 2 * d : d;
+  // row width of the point set; PDEIP_DRIFT_IN_POINTS appends grad V_true (d floats) to every point
+  const int dim = (kinetic ? 2 * d : d) + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);
+  const int gt_off = kinetic ? 2 * d : d;
   const int64_t tile_pts = NW * 32;
   const int64_t n_tiles = (a.n_points + tile_pts - 1) / tile_pts;
 
@@ -104,7 +106,12 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp_residual_kernel(const Residual
     if (SET == PDEIP_SET_KFP_0T || SET == PDEIP_SET_FP_0T) {
       float g[kDMax], gt[kDMax];
       net.input_gradient(g);
-      true_grad_thread(a.tg, tp, d, st.x, gt);
+      if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+        for (int i = 0; i < d; ++i)
+          gt[i] = valid ? a.points[elem_index(a.layout, p, gt_off + i, a.n_points, dim)] : 0.f;
+      } else {
+        true_grad_thread(a.tg, tp, d, st.x, gt);
+      }
       float g2 = 0.f, gt2 = 0.f, gd2 = 0.f;
       for (int i = 0; i < d; ++i) {
         g2 = fmaf(g[i], g[i], g2);

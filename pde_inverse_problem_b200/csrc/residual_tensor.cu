@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     const float gamma = a.coef;
     const int cg4 = sub;  // the chunk of a 32-unit tile owned by this thread
     // this thread's x|v input chunk (sub-warps with sub < 2*DP/8 own one), prefetched one tile ahead
+    const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
     const bool has_in = sub < 2 * (DP / 8);
     const int in_band = sub / (DP / 8), in_cg = sub % (DP / 8);
     float xin[8];
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int u = in_cg * 8 + i;
-        xin[i] = (ok_p && u < d) ? __ldg(a.points + elem_index(a.layout, pp, in_band * d + u, a.n_points, 2 * d)) : 0.f;
+        xin[i] = (ok_p && u < d) ? __ldg(a.points + elem_index(a.layout, pp, in_band * d + u, a.n_points, dimw)) : 0.f;
       }
     };
     load_inputs(blockIdx.x);
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
         float x[DP];
 #pragma unroll
         for (int u = 0; u < DP; ++u)
-          x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, 2 * d)) : 0.f;
+          x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
         float m = -INFINITY, se = 0.f, accg[DP];
 #pragma unroll
         for (int u = 0; u < DP; ++u) accg[u] = 0.f;
@@ -677,9 +678,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 #pragma unroll
           for (int i = 0; i < 8; ++i) gq[cg * 8 + i] = gv[i];
         }
+        if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
 #pragma unroll
-        for (int u = 0; u < DP; ++u)
-          x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, 2 * d)) : 0.f;
+          for (int u = 0; u < DP; ++u)
+            x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
+        }
         float g2 = 0.f, gt2 = 0.f, gd2 = 0.f;
         if (a.tg.kind == PDEIP_DRIFT_GMM) {
           float ms[8];
@@ -714,7 +717,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
           for (int u = 0; u < DP; ++u) {
             if ((u & 3) == sub && u < d) {
               float gti = 0.f;
-              if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
+              if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {  // stored next to the point by the integrator
+                gti = valid ? __ldg(a.points + elem_index(a.layout, p, 2 * d + u, a.n_points, dimw)) : 0.f;
+              } else if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
 #pragma unroll
                 for (int k = 0; k < DP; ++k)
                   if (k < d) gti = fmaf(tp[u * d + k], x[k], gti);

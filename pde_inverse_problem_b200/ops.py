@@ -48,8 +48,10 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
                  state_layout: int = L.LAYOUT_AOS, traj_layout: int = L.TRAJ_PARTICLE_MAJOR,
                  want_traj: bool = True, want_tau: bool = False, emit_every: int = 1, emit_offset: int = 0,
                  traj_out: Optional[torch.Tensor] = None, z_last_out: Optional[torch.Tensor] = None,
+                 emit_drift: bool = False,
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """pdeip_kl_integrate.  z0: [N,2d] (AOS) or [2d,N] (SOA).  Returns (z_last, traj|None, tau|None)."""
+    """pdeip_kl_integrate.  z0: [N,2d] (AOS) or [2d,N] (SOA).  Returns (z_last, traj|None, tau|None).
+    emit_drift: every trajectory sample is [x, v, grad U(x)] (3d components)."""
     lib = L.load()
     z0 = _f32(z0, "z0")
     if state_layout == L.LAYOUT_AOS:
@@ -69,19 +71,20 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
     s_emit = (n_steps - emit_offset + emit_every - 1) // emit_every
     traj = None
     if want_traj:
-        shape = {L.TRAJ_PARTICLE_MAJOR: (n, s_emit, two_d), L.TRAJ_TIME_MAJOR: (s_emit, n, two_d),
-                 L.TRAJ_TIME_SOA: (two_d, s_emit, n)}[traj_layout]
+        width = two_d + d if emit_drift else two_d
+        shape = {L.TRAJ_PARTICLE_MAJOR: (n, s_emit, width), L.TRAJ_TIME_MAJOR: (s_emit, n, width),
+                 L.TRAJ_TIME_SOA: (width, s_emit, n)}[traj_layout]
         if traj_out is not None:
-            if traj_out.numel() < n * s_emit * two_d:
+            if traj_out.numel() < n * s_emit * width:
                 raise PdeipError("traj_out too small")
-            traj = _f32(traj_out, "traj_out").view(-1)[: n * s_emit * two_d].view(shape)
+            traj = _f32(traj_out, "traj_out").view(-1)[: n * s_emit * width].view(shape)
         else:
             traj = torch.empty(shape, device=z0.device, dtype=torch.float32)
     tau = torch.empty((n, n_steps), device=z0.device, dtype=torch.float32) if want_tau else None
     st = lib.pdeip_kl_integrate(_ptr(z0), _ptr(z_last), _ptr(traj), _ptr(tau), n, d, n_steps, dt, gamma,
                                 drift_kind, _ptr(drift_params), n_gaussian, sigma, _ptr(noise), _ptr(tau0),
                                 seed & 0xFFFFFFFFFFFFFFFF, particle_offset, step_offset, schedule, state_layout,
-                                traj_layout, emit_every, emit_offset, _stream())
+                                traj_layout, emit_every, emit_offset, 1 if emit_drift else 0, _stream())
     L.check(st, "pdeip_kl_integrate")
     launch_counter["n"] += 1
     return z_last, traj, tau
@@ -232,7 +235,7 @@ class TrueGrad:
 
     def __init__(self, kind: int = L.DRIFT_NONE, params: Optional[torch.Tensor] = None, sigma: float = 1.0):
         self.kind = kind
-        self.params = _f32(params, "true_params", allow_none=(kind == L.DRIFT_NONE))
+        self.params = _f32(params, "true_params", allow_none=(kind in (L.DRIFT_NONE, L.DRIFT_IN_POINTS)))
         self.n_gaussian = int(self.params.shape[0]) if kind == L.DRIFT_GMM else 0
         self.sigma = float(sigma)
 
@@ -262,6 +265,8 @@ class ResidualAccumulator:
             raise PdeipError(f"params has {params.numel()} entries, expected {self.spec.num_params}")
         kinetic = set_kind in (L.SET_KFP_0T, L.SET_KFP_BOUNDARY)
         dim = 2 * self.spec.d if kinetic else self.spec.d
+        if true_grad is not None and true_grad.kind == L.DRIFT_IN_POINTS:
+            dim += self.spec.d  # grad V_true stored after the point's own components
         if n_points is None:
             if layout == L.LAYOUT_AOS:
                 if points.ndim != 2 or points.shape[1] != dim:

@@ -45,7 +45,9 @@ class HotPath:
         self.norms = torch.empty(2, device=self.device, dtype=torch.float32)
         s_emit = (cfg.n_steps + cfg.emit_every - 1) // cfg.emit_every
         self.s_emit = s_emit
-        self.traj = torch.empty(2 * cfg.d * s_emit * cfg.chunk, device=self.device, dtype=torch.float32)
+        # every sample carries [x, v, grad U(x)]: the integrator emits the drift it evaluates anyway
+        self.traj = torch.empty(3 * cfg.d * s_emit * cfg.chunk, device=self.device, dtype=torch.float32)
+        self.true_in_points = ops.TrueGrad(L.DRIFT_IN_POINTS)
         self.z_last = torch.empty((cfg.chunk, 2 * cfg.d), device=self.device, dtype=torch.float32)
         self.z_stage = torch.empty((cfg.chunk, 2 * cfg.d), device=self.device, dtype=torch.float32)
 
@@ -79,9 +81,9 @@ class HotPath:
             z_last, traj, _ = ops.kl_integrate(
                 zc, c.n_steps, dt, c.gamma, c.drift_kind, self.drift_params, n_gaussian=c.n_gaussian, sigma=c.sigma,
                 seed=seed, particle_offset=particle_offset + lo, traj_layout=L.TRAJ_TIME_SOA,
-                emit_every=c.emit_every, traj_out=self.traj, z_last_out=self.z_last[:nc])
-            self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(2 * c.d, self.s_emit * nc), w_0T, coef=c.gamma,
-                                layout=L.LAYOUT_SOA, true_grad=self.true_grad, path=c.path)
+                emit_every=c.emit_every, traj_out=self.traj, z_last_out=self.z_last[:nc], emit_drift=True)
+            self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * c.d, self.s_emit * nc), w_0T, coef=c.gamma,
+                                layout=L.LAYOUT_SOA, true_grad=self.true_in_points, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, z_last, w_b, coef=2.0 / c.total_time, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, zc, w_b, coef=-2.0 / c.total_time, path=c.path)
         sums, grad = self.acc.finalize()

@@ -28,7 +28,7 @@ def test_argument_validation_without_gpu():
     from pde_inverse_problem_b200 import _lib as L
     lib = L.load()
     st = lib.pdeip_kl_integrate(None, None, None, None, 10, 4, 5, 0.1, 1.0, L.DRIFT_NONE, None, 0, 1.0, None, None,
-                                0, 0, 0, 0, 0, 0, 1, 0, None)
+                                0, 0, 0, 0, 0, 0, 1, 0, 0, None)
     assert st == -1 and b"z0" in lib.pdeip_last_error()
     st = lib.pdeip_gmm_value_grad(1, 1, 3, 1.0, None, None, 10, 64, None)   # d > 32
     assert st == -2 and b"32" in lib.pdeip_last_error()

@@ -211,3 +211,33 @@ def test_ou_ensemble_moments_match_discrete_recursion(cuda):
     # moments kernel vs torch
     zc = zl.double()
     assert relmax(s2, (zc.T @ zc)) < 1e-4
+
+
+@pytest.mark.parametrize("layout", ["particle", "time", "soa"])
+def test_emit_drift_carries_grad_U_of_every_sample(cuda, layout):
+    """emit_drift: each sample is [x, v, grad U(x)] — the drift the integrator evaluates at the following step."""
+    ops, L = _ops()
+    d, K, N, S, dt, gamma = 8, 5, 300, 12, 0.02, 0.5
+    z0, noise, tau0, mus = _setup_traj(d, K, N, S, seed=21)
+    tau0 = tau0 * dt
+    lay = {"particle": L.TRAJ_PARTICLE_MAJOR, "time": L.TRAJ_TIME_MAJOR, "soa": L.TRAJ_TIME_SOA}[layout]
+    _, traj64, _ = o_int.underdamped_langevin_dynamics_scan(z0, S, dt, noise, tau0, o_pot.GMMPotential(mus, 1.0).gradient, gamma)
+    zl, tr, _ = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_GMM, mus.float().to(cuda), n_gaussian=K,
+                                 noise=noise.float().to(cuda), tau0=tau0.float().to(cuda), traj_layout=lay,
+                                 emit_drift=True, emit_every=3, emit_offset=1)
+    if layout == "time":
+        tr = tr.permute(1, 0, 2)
+    elif layout == "soa":
+        tr = tr.permute(2, 1, 0)
+    assert tr.shape == (N, 4, 3 * d)
+    ref = traj64[:, 1::3]
+    assert relmax(tr[..., : 2 * d], ref) < 1e-5
+    gref = o_pot.vg_gmm_V(ref[..., :d].reshape(-1, d), mus, 1.0).reshape(N, 4, d)
+    assert relmax(tr[..., 2 * d:], gref) < 1e-5
+    # UNIFORM schedule: the last sample has no following step, its drift is evaluated separately
+    zl, tr, _ = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_GMM, mus.float().to(cuda), n_gaussian=K,
+                                 noise=noise[:, :S].float().contiguous().to(cuda), schedule=L.SCHEDULE_UNIFORM,
+                                 traj_layout=L.TRAJ_PARTICLE_MAJOR, emit_drift=True)
+    x_last = tr[:, -1, :d].double().cpu()
+    assert relmax(tr[:, -1, 2 * d:], o_pot.vg_gmm_V(x_last, mus, 1.0)) < 1e-5
+    assert relmax(tr[:, -1, : 2 * d], zl) < 1e-7

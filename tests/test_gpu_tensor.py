@@ -86,3 +86,29 @@ def test_tensor_path_matches_fp32_path_many_tiles(cuda):
     # run twice: bit-identical (no atomics across CTAs, fixed reduction order)
     stc2, gtc2 = _run(ops, L, cuda, spec, flat, pts.t().contiguous(), n, 0.5, tg, L.PATH_TENSOR, layout=L.LAYOUT_SOA)
     assert torch.equal(gtc, gtc2)
+
+
+@pytest.mark.parametrize("path_name", ["fp32", "tensor"])
+def test_true_gradient_stored_in_points(cuda, path_name):
+    """PDEIP_DRIFT_IN_POINTS ([x, v, grad V_true] per point, as emitted by the integrator) gives the same sums as
+    the inline true gradient."""
+    ops, L = _ops()
+    d, K, n = 8, 16, 9000
+    path = L.PATH_FP32 if path_name == "fp32" else L.PATH_TENSOR
+    p = _params(d)
+    flat = o_model.flatten_params(p).float().to(cuda)
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.randn(n, 2 * d, generator=g) * 1.5).to(cuda)
+    mus = (torch.rand(K, d, generator=g) * 8 - 4).to(cuda)
+    _, gt = ops.gmm_value_grad(pts[:, :d].contiguous(), mus, 1.0)
+    spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
+    s_a, g_a = _run(ops, L, cuda, spec, flat, pts, n, 0.5, ops.TrueGrad(L.DRIFT_GMM, mus, 1.0), path)
+    pts3 = torch.cat([pts, gt], 1).contiguous()
+    s_b, g_b = _run(ops, L, cuda, spec, flat, pts3, n, 0.5, ops.TrueGrad(L.DRIFT_IN_POINTS), path)
+    s_c, g_c = _run(ops, L, cuda, spec, flat, pts3.t().contiguous(), n, 0.5, ops.TrueGrad(L.DRIFT_IN_POINTS), path,
+                    layout=L.LAYOUT_SOA)
+    for s_x, g_x in ((s_b, g_b), (s_c, g_c)):
+        assert relmax(s_x[L.SUM_LOSS], s_a[L.SUM_LOSS]) < 1e-5
+        assert relmax(s_x[L.SUM_GT], s_a[L.SUM_GT]) < 1e-5
+        assert relmax(s_x[L.SUM_GTRUE2], s_a[L.SUM_GTRUE2]) < 1e-5
+        assert relmax(g_x, g_a) < 1e-5
