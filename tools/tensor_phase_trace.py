@@ -1,5 +1,5 @@
 import sys, ctypes as C, torch
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pde_inverse_problem_b200 import ops, _lib as L
 from oracle import model as o_model
 cuda = torch.device('cuda')
