@@ -1,22 +1,30 @@
-// residual_tensor.cu — K3/K4 on the 5th-generation tensor cores (tcgen05 + TMEM), KFP 0T point set.
+// residual_tensor.cu — K3/K4 on the 5th-generation tensor cores (tcgen05 + TMEM), KFP 0T point set, version 2.
 //
-// Same mathematics as residual_mlp.cu (reference: kinetic_fokker_planck.py:11-69), organised as a
-// chain of 128-point x {32,48}-unit GEMMs:  one CTA = 128 threads = one 128-point tile at a time, thread p owns
-// point p (TMEM lane p) in every epilogue, one elected thread issues the MMAs.
+// Mathematics: SURVEY.md §9 (reference: methods/consistency_instances/kinetic_fokker_planck.py:11-69), restated
+// phase by phase in tests/tensor_v2_model.py (float64 twin, checked against oracle/taylor.py to 1e-16).
+// Per point (x, v):  l = |g|^2 - 2 D_v^2 V + 2 gamma D_v V,  g = grad_x V,  V = |MLP(x)|^2,  and dl/dtheta.
 //
-//   operands   bf16 in shared memory, no-swizzle core-matrix layout (umma.cuh); every tile is written once and
-//              used both K-major (layer GEMMs: points x units) and through the transposed view (batch-reduced
-//              dW GEMMs: units x points).  Weights are split W = W_hi + W_lo (two bf16 MMAs per k-step), which
-//              removes the systematic weight-rounding error; activations are rounded to bf16 once.
-//   accumulators  fp32 in TMEM; epilogues (tanh, s1 = 1-t^2, s2, Taylor-stream and adjoint updates) in fp32.
-//   phases     S0 x,v -> z0, z1_0 | S1 t1,a1,a2 -> z1, z1_1, z2_1 | S2 t2,a1,a2 -> u,u1,u2 | S3-S5 input-gradient
-//              chain -> g | S6-S8 stop-gradient stream along g -> ug | S9 seeds -> abar (layer 2) + dW2 + db2 |
-//              S10 tanh-reverse -> abar (layer 1) + dW1 + db1 | S11 tanh-reverse -> dW0 + db0 | S12 read-out.
-//   dW         D[(stream,unit_in)][unit_out] = sum_points ACT^T Zbar_s with the 4 streams stacked along M; only
-//              the band of stream s is meaningful in region s, and that band is exactly the TMEM lane quadrant
-//              of warp s, so each warp reads back 32 lanes x N columns per tile and keeps the running sums in
-//              registers.  db_l comes from a constant-one unit in the x|v|g tile (persistent TMEM regions).
-//   parity     rtol 1e-2 (BASELINE.json, bf16 GEMM path); measured against the oracle in tests/test_gpu_tensor.py.
+// Organisation.  One CTA per SM, persistent over 128-point tiles; NS tiles ("slots") are in flight per CTA so
+// that one slot's epilogue hides the other's GEMM hand-off latency (NS = 2 for d <= 8, 1 otherwise).
+//   * 16 epilogue warps: thread = (point row == TMEM lane, 8-unit chunk); 1 MMA warp: one elected lane issues
+//     every tcgen05.mma of both slots.
+//   * operands: bf16 in shared memory, no-swizzle core-matrix layout (umma.cuh); every tile is written once and
+//     used K-major (layer GEMMs, points x units) and through the transposed view (batch-reduced dW GEMMs).
+//     Weights and the input x are split hi + lo (two bf16 terms), activations are rounded to bf16 once.
+//   * accumulators: fp32 in TMEM.  Values an epilogue needs again later are "parked" in TMEM as packed bf16 pairs
+//     (s1 = 1 - t^2 of both hidden layers, the partial seed s0p, the pz terms).
+//   * streams.  Forward Taylor streams along v: a (primal), a1, a2~ = -2 a2.  Input gradient chain za_l / aa_l.
+//     Stop-gradient stream along g~ = 2 g (order 1).  The adjoints of the a2 and g streams are proportional to the
+//     input-gradient chain (zbar2 = -2 za, zbar_g = 2 za), so only TWO adjoint streams need GEMMs: the primal
+//     (zbar0) and the order-1 stream (zbar1); the latter rides along with the input-gradient chain (P3..P5).
+//   * dW_l = t^T zbar0 + a1^T zbar1 + (a2~ + ag~)^T za accumulates over ALL tiles of the CTA in persistent TMEM
+//     columns: each term is an M = 128 GEMM over the 128 points whose A operand is the transposed view of the
+//     activation tile started at the band of that stream ("band-shifted accumulate"): rows 0..31 of D are the
+//     wanted 32 x N block, rows >= 32 are never read.  db_l = sum_p zbar0 is kept in registers.
+//   phases  P0 z0,z1_0 | P1 z1,z1_1,z2~_1 | P2 u,u1,u2~ | P3 aa2, ab1_2 (+dW2: a1) | P4 aa1, ab1_1 (+dW1: a1) |
+//           P5 g (+dW0: v) | P6 zg~_0 | P7 zg~_1 | P8 ug~ | P9 ab_2, aa2 (+dW2: t, c) | P10 ab_1, aa1 (+dW1: t, c) |
+//           P11 (dW0: x_hi, x_lo, g~).   E_k = epilogue between P_{k-1} and P_k.
+//   parity  rtol 1e-2 (BASELINE.json, bf16 GEMM path); measured against the oracle in tests/test_gpu_tensor.py.
 #include "mlp_thread.cuh"
 #include "residual_common.cuh"
 #include "umma.cuh"
@@ -32,156 +40,139 @@ using namespace umma;
 constexpr int H = 32;
 constexpr int OP = 48;  // output width 40 padded to a multiple of 16
 
-// TMEM column map (512 columns allocated)
-constexpr uint32_t C_T1 = 0, C_T2 = 32, C_DB2 = 64, C_DB1 = 112;   // persistent
-constexpr uint32_t C_Z10 = 144, C_Z11 = 176, C_Z21 = 208;            // S0/S1 transients
-constexpr uint32_t C_U = 144, C_U1 = 192, C_U2 = 240, C_UG = 288;    // S2..S9
-constexpr uint32_t C_AA2 = 336, C_AA1 = 368, C_G = 400, C_ZG0 = 432, C_ZG1 = 464;
-constexpr uint32_t C_GX = 432, C_GMS = 496;  // S3..S6: GMM true-gradient partials (acc[sub][DP], (m,se)[sub])
-constexpr uint32_t C_DW = 144;   // dW regions of the reverse phases
-constexpr uint32_t C_AB = 336;   // abar_s regions: C_AB + 32 s
+// ---- TMEM column map: [0, 112) persistent dW accumulators, then NS slots of 200 columns -----------------------
+constexpr uint32_t C_DW2 = 0, C_DW1 = 48, C_DW0 = 80, C_SLOT0 = 112, SLOT_COLS = 200;
+// slot-relative
+constexpr uint32_t C_S1P1 = 0, C_S1P2 = 16;  // parked s1 of hidden layers 1 / 2 (packed bf16 pairs, 16 columns)
+constexpr uint32_t C_R = 32;                  // 144 transient columns
+constexpr uint32_t C_Z0 = C_R + 0, C_Z10 = C_R + 32;                       // P0
+constexpr uint32_t C_Z1 = C_R + 64, C_Z11 = C_R + 96, C_Z21 = C_R + 0;      // P1
+constexpr uint32_t C_U = C_R + 0, C_U1 = C_R + 48, C_U2 = C_R + 96;         // P2
+constexpr uint32_t C_S0P = 176;                                            // parked s0p (24 columns)
+constexpr uint32_t C_AA2 = C_R + 0, C_AB12 = C_R + 32, C_PZ2 = C_R + 128;   // P3 / E4
+constexpr uint32_t C_AA1 = C_R + 64, C_AB11 = C_R + 96, C_PZ1 = C_R + 0;    // P4 / E5
+constexpr uint32_t C_G = C_R + 16;                                         // P5
+constexpr uint32_t C_ZG0 = C_R + 64, C_ZG1 = C_R + 96, C_UG = C_R + 48;     // P6, P7, P8
+constexpr uint32_t C_AB2 = C_R + 16, C_AA2R = C_R + 96;                     // P9
+constexpr uint32_t C_AB1 = C_R + 48, C_AA1R = C_R + 96;                     // P10
 
-template <int DP>
-struct Smem {
-  static constexpr uint32_t RG_T0 = DP / 8 * 128, RG_T1 = 512, RG_T2 = 512;
-  static constexpr uint32_t SZ_T0 = 4 * RG_T0, SZ_T1 = 4 * RG_T1, SZ_T2 = 6 * RG_T2;
-  static constexpr uint32_t RG_X = 4 * DP / 8 * 128, SZ_X = 16 * RG_X;
-  static constexpr uint32_t RG_A = 2048, SZ_A = 16 * RG_A;
-  static constexpr uint32_t RG_Z = 4 * OP / 8 * 128, SZ_Z = 16 * RG_Z;
-  static constexpr uint32_t O_T0H = 0, O_T0L = O_T0H + SZ_T0, O_T1H = O_T0L + SZ_T0, O_T1L = O_T1H + SZ_T1,
+// ---- shared memory ---------------------------------------------------------------------------------------------
+// Z tile chunk map (24 chunks of 8 columns)
+constexpr int ZC_ZA2 = 0, ZC_ZA1 = 6, ZC_ZA0 = 10, ZC_TA = 14, ZC_TB = 20;
+// A tile chunk map (12 chunks): t | a1 (later the g-stream operand ag~) | a2~ (later c = a2~ + ag~)
+constexpr int AC_T = 0, AC_A1 = 4, AC_C = 8;
+
+template <int DP, int NS>
+struct Cfg {
+  static constexpr int XC = DP / 8;                  // chunks per input band
+  static constexpr int NX = 4 * XC;                  // x_hi | x_lo | v | g~
+  static constexpr int KX = 2 * DP;                  // K of the x GEMM ([x_hi | x_lo] against [W0; W0])
+  static constexpr int KV = DP < 16 ? 16 : DP;       // K of the v / g~ GEMMs, N of the g GEMM
+  static constexpr int XC_HI = 0, XC_LO = XC, XC_V = 2 * XC, XC_G = 3 * XC;
+  static constexpr uint32_t RG_X = NX * 128, RG_A = 12 * 128, RG_Z = 24 * 128;
+  static constexpr uint32_t SZ_X = 16 * RG_X, SZ_A = 16 * RG_A, SZ_Z = 16 * RG_Z;
+  static constexpr uint32_t O_X = 0, O_A1 = O_X + SZ_X, O_A2 = O_A1 + SZ_A, O_Z = O_A2 + SZ_A, SLOT = O_Z + SZ_Z;
+  // weights (rows = output units, columns = input units), hi and lo halves
+  static constexpr uint32_t RG_T0X = KX / 8 * 128, SZ_T0X = 4 * RG_T0X;
+  static constexpr uint32_t RG_T0V = KV / 8 * 128, SZ_T0V = 4 * RG_T0V;
+  static constexpr uint32_t RG_T1 = 512, SZ_T1 = 4 * RG_T1, RG_T2 = 512, SZ_T2 = 6 * RG_T2;
+  static constexpr uint32_t O_T0XH = NS * SLOT, O_T0XL = O_T0XH + SZ_T0X, O_T0VH = O_T0XL + SZ_T0X,
+                            O_T0VL = O_T0VH + SZ_T0V, O_T1H = O_T0VL + SZ_T0V, O_T1L = O_T1H + SZ_T1,
                             O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2, O_BIAS = O_T2L + SZ_T2;
-  static constexpr uint32_t O_X = O_BIAS + 512, O_A1 = O_X + SZ_X, O_A2 = O_A1 + SZ_A, O_Z = O_A2 + SZ_A;
-  static constexpr uint32_t O_STASH = O_Z + SZ_Z, SZ_STASH = 5 * 32 * 128 * 4;
-  static constexpr uint32_t O_TRUE = O_STASH + SZ_STASH, SZ_TRUE = 4096;
-  static constexpr uint32_t O_MISC = O_TRUE + SZ_TRUE, TOTAL = O_MISC + 64;
+  static constexpr uint32_t TP_BYTES = NS == 2 ? 2048 : 4096;
+  static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
+  // prefetched input items per thread: x chunks, v chunks, (stored true gradient chunks), dealt round-robin to sub
+  static constexpr int NI = (3 * XC + 3) / 4;
 };
-
-// stash arrays (fp32 [unit][point])
-enum { ST_Z10 = 0, ST_ZG0 = 1, ST_Z11 = 2, ST_Z21 = 3, ST_ZG1 = 4 };
-
-struct Ctx {
-  uint32_t tbase;      // TMEM base (lane 0)
-  uint32_t lane_addr;  // TMEM address of this thread's lane quadrant
-  uint32_t mb_fast;    // mbarrier: the GEMMs the next epilogue depends on have completed
-  uint32_t mb_dw;      // mbarrier: the batch-reduced dW GEMMs of the phase have completed
-  uint32_t par_fast, par_dw;
-  int* status;
-  bool ok;
-};
-
-#ifdef PDEIP_TC_TRACE
-#define TC_TRACE(slot, ph) do { if (trace_on) trace[(ph) * 4 + (slot)] = clock64(); } while (0)
-#else
-#define TC_TRACE(slot, ph) do { } while (0)
-#endif
 
 constexpr int kEpiThreads = 512;            // 16 epilogue warps: thread = (point row, 8-unit chunk)
 constexpr int kThreads = kEpiThreads + 32;  // + one MMA-issuing warp
 
-// epilogue side: operands written -> visible to the tensor core; TMEM reads ordered; signal the MMA warp
-__device__ __forceinline__ void epi_arrive() {
+#ifdef PDEIP_TC_PROBE
+#define TC_PROBE(id, unit0, arr)                                                              \
+  do {                                                                                        \
+    if (probe_on) {                                                                           \
+      for (int _i = 0; _i < 8; ++_i) probe[((id) * 128 + row) * 48 + (unit0) + _i] = (arr)[_i]; \
+    }                                                                                         \
+  } while (0)
+#else
+#define TC_PROBE(id, unit0, arr) do { } while (0)
+#endif
+
+// epilogue side: operands written -> visible to the tensor core; TMEM accesses ordered; signal the MMA warp
+__device__ __forceinline__ void epi_arrive(int slot) {
   fence_async_smem();
   fence_before_sync();
-  asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "n"(kThreads) : "memory");
 }
 // MMA warp: wait until every epilogue thread has arrived
-__device__ __forceinline__ void mma_wait_operands() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+__device__ __forceinline__ void mma_wait_operands(int slot) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(kThreads) : "memory");
   fence_after_sync();
 }
 
-__device__ __forceinline__ void wait_fast(Ctx& c) {
-  if (c.ok && !mbar_wait(c.mb_fast, c.par_fast)) {
-    c.ok = false;
-    atomicExch(c.status, 1);
-  }
-  c.par_fast ^= 1u;
-  fence_after_sync();
+// ---- descriptors as (lo, hi) 32-bit halves; advancing = one add on lo (addresses stay below 256 KB) ----------
+struct Desc {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ Desc mk_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  Desc d;
+  d.lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // descriptor version 1 (bit 46)
+  return d;
 }
-__device__ __forceinline__ void wait_dw(Ctx& c) {
-  if (c.ok && !mbar_wait(c.mb_dw, c.par_dw)) {
-    c.ok = false;
-    atomicExch(c.status, 1);
-  }
-  c.par_dw ^= 1u;
-  fence_after_sync();
+__device__ __forceinline__ void mma(uint32_t d_tmem, Desc a, uint32_t a_adv, Desc b, uint32_t b_adv, uint32_t idesc,
+                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a.lo + (a_adv >> 4)), "r"(a.hi), "r"(b.lo + (b_adv >> 4)), "r"(b.hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-// ---- MMA-warp side: descriptors are built once; advancing a descriptor by `bytes` is one 32-bit add on the
-// start-address field (addresses stay below 256 KB, so there is no carry out of the field) ---------------
-__device__ __forceinline__ uint64_t adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
-
-// D[128 x N] (+)= A(K-major, K cols from a_k) * B(K-major weight tile [N][K]); hi + lo halves of the weights
-template <int K, int N>
-__device__ __forceinline__ void mm_fwd(uint32_t d, uint64_t a_k, uint64_t w_hi_k, uint64_t w_lo_k) {
-  constexpr uint32_t idesc = make_idesc(N, 0, 0);
-#pragma unroll
-  for (int k = 0; k < K; k += 16) mma_bf16(d, adv(a_k, k * 16), adv(w_hi_k, k * 16), idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-  for (int k = 0; k < K; k += 16) mma_bf16(d, adv(a_k, k * 16), adv(w_lo_k, k * 16), idesc, 1u);
-}
-// NG independent GEMMs (different D, different A column offsets, same weights) issued round-robin so that
-// consecutive MMAs never accumulate into the same TMEM region (dependent accumulation costs a full pipeline latency)
+// NG independent forward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W^T(K-major tile [N][K]), hi + lo halves of
+// the weights, issued round-robin over g.  a_off[g] / d[g]: byte offset of the A band / TMEM column of GEMM g.
 template <int K, int N, int NG>
-__device__ __forceinline__ void mm_fwd_multi(uint32_t d0, uint32_t d_stride, uint64_t a_k, uint32_t a_stride_bytes,
-                                             uint64_t w_hi_k, uint64_t w_lo_k) {
+__device__ __forceinline__ void mm_fwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi, Desc w_lo) {
   constexpr uint32_t idesc = make_idesc(N, 0, 0);
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
-      mma_bf16(d0 + g * d_stride, adv(a_k, g * a_stride_bytes + k * 16), adv(w_hi_k, k * 16), idesc, k > 0 ? 1u : 0u);
+    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi, k * 16, idesc, k > 0 ? 1u : 0u);
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
-      mma_bf16(d0 + g * d_stride, adv(a_k, g * a_stride_bytes + k * 16), adv(w_lo_k, k * 16), idesc, 1u);
+    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
 }
+// NG backward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W (transposed view of the weight tile, rows = K)
 template <int K, int N, int NG>
-__device__ __forceinline__ void mm_bwd_multi(uint32_t d0, uint32_t d_stride, uint64_t a_k, uint32_t a_stride_bytes,
-                                             uint64_t w_hi_m, uint64_t w_lo_m, uint32_t w_rg) {
+__device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi_m,
+                                       Desc w_lo_m, uint32_t w_rg) {
   constexpr uint32_t idesc = make_idesc(N, 0, 1);
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
-      mma_bf16(d0 + g * d_stride, adv(a_k, g * a_stride_bytes + k * 16), adv(w_hi_m, (k >> 3) * w_rg), idesc, k > 0 ? 1u : 0u);
+    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi_m, (k >> 3) * w_rg, idesc, k > 0 ? 1u : 0u);
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
-      mma_bf16(d0 + g * d_stride, adv(a_k, g * a_stride_bytes + k * 16), adv(w_lo_m, (k >> 3) * w_rg), idesc, 1u);
+    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo_m, (k >> 3) * w_rg, idesc, 1u);
 }
-// NG batch-reduced outer products sharing the A operand, round-robin over the B operands / D regions
-template <int N, int NG>
-__device__ __forceinline__ void mm_outer_multi(uint32_t d0, uint32_t d_stride, uint64_t a_m, uint32_t a_rg, uint64_t b_m,
-                                               uint32_t b_stride_bytes, uint32_t b_rg) {
-  constexpr uint32_t idesc = make_idesc(N, 1, 1);
-#pragma unroll
-  for (int k = 0; k < 128; k += 16)
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-      mma_bf16(d0 + g * d_stride, adv(a_m, (k >> 3) * a_rg), adv(b_m, g * b_stride_bytes + (k >> 3) * b_rg), idesc,
-               k > 0 ? 1u : 0u);
-}
-
-// D[128 x N] = A(K-major) * W^T (transposed view of the weight tile: operand rows = tile columns)
-template <int K, int N>
-__device__ __forceinline__ void mm_bwd(uint32_t d, uint64_t a_k, uint64_t w_hi_m, uint64_t w_lo_m, uint32_t w_rg) {
-  constexpr uint32_t idesc = make_idesc(N, 0, 1);
-#pragma unroll
-  for (int k = 0; k < K; k += 16) mma_bf16(d, adv(a_k, k * 16), adv(w_hi_m, (k >> 3) * w_rg), idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-  for (int k = 0; k < K; k += 16) mma_bf16(d, adv(a_k, k * 16), adv(w_lo_m, (k >> 3) * w_rg), idesc, 1u);
-}
-// D[128 x N] (+)= A^T B over the 128 points (both transposed views)
+// band-shifted batch-reduced outer product: D[m][n] += sum_points A[p][a_col0 + m] * B[p][b_col0 + n]
+// (both operands transposed views; a_off / b_off = byte offsets of the first chunk of the band)
 template <int N>
-__device__ __forceinline__ void mm_outer(uint32_t d, uint64_t a_m, uint32_t a_rg, uint64_t b_m, uint32_t b_rg,
-                                         uint32_t accumulate) {
+__device__ __forceinline__ void mm_outer(uint32_t d, Desc a_m, uint32_t a_off, uint32_t a_rg, Desc b_m, uint32_t b_off,
+                                         uint32_t b_rg, uint32_t accumulate) {
   constexpr uint32_t idesc = make_idesc(N, 1, 1);
 #pragma unroll
   for (int k = 0; k < 128; k += 16)
-    mma_bf16(d, adv(a_m, (k >> 3) * a_rg), adv(b_m, (k >> 3) * b_rg), idesc, k > 0 ? 1u : accumulate);
+    mma(d, a_m, a_off + (k >> 3) * a_rg, b_m, b_off + (k >> 3) * b_rg, idesc, k > 0 ? 1u : accumulate);
 }
 
 // MUFU tanh (max relative error ~2^-11, below the bf16 rounding applied to every activation operand)
@@ -191,38 +182,77 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
+// ---- packed bf16 helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+__device__ __forceinline__ void load_chunk(const uint8_t* tile, uint32_t off, float (&v)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(tile + off), v);
+}
+// park 8 floats as 4 TMEM columns of packed bf16 pairs / read them back
+__device__ __forceinline__ void tmem_park8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n\t"
+      "tcgen05.wait::st.sync.aligned;\n" ::"r"(taddr),
+      "r"(pack2(v[0], v[1])), "r"(pack2(v[2], v[3])), "r"(pack2(v[4], v[5])), "r"(pack2(v[6], v[7]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_raw(uint32_t taddr, uint4& q) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\t"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, float (&v)[8]) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "r"(taddr)
+               : "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int DP>
+template <int DP, int NS>
 __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
-  using S = Smem<DP>;
+  using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma_warp = warp == kEpiThreads / 32;
-  const int q = warp & 3;     // TMEM lane quadrant of this warp
-  const int sub = warp >> 2;  // which 8-unit chunk(s) this thread owns (epilogue warps: 0..3)
+  const int q = warp & 3;         // TMEM lane quadrant of this warp
+  const int sub = warp >> 2;      // which 8-unit chunk(s) this thread owns (epilogue warps: 0..3)
   const int row = q * 32 + lane;  // point within the tile == TMEM lane == operand tile row
   const int d = a.d;
   const MlpShape<H> sh{d, 2};
   const int P = sh.num_params();
   float* bias_s = reinterpret_cast<float*>(sm + S::O_BIAS);   // b0[32] b1[32] b2[48]
-  float* stash = reinterpret_cast<float*>(sm + S::O_STASH);
   float* tp = reinterpret_cast<float*>(sm + S::O_TRUE);
-  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(sm + S::O_MISC);  // [0] fast, [1] dw
-  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(sm + S::O_MISC + 16);
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(sm + S::O_MISC);  // [slot]
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(sm + S::O_MISC + 64);
 
   const int64_t n_tiles = (a.n_points + 127) / 128;
-  if ((int64_t)blockIdx.x >= n_tiles) return;  // nothing to do for this CTA (uniform)
+  if ((int64_t)blockIdx.x * NS >= n_tiles) return;  // nothing to do for this CTA (uniform)
 
-  // ---- one-time set-up: TMEM, mbarriers, split weights in core-matrix layout, constants ------------------
+  // ---- one-time set-up: TMEM, mbarriers, zeroed operand tiles, split weights in core-matrix layout ------------
   if (warp == 0) {
     tmem_alloc(smem_u32(tmem_p), 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    mbar_init(smem_u32(mbar_p), 1);
-    mbar_init(smem_u32(mbar_p + 1), 1);
+    for (int s = 0; s < NS; ++s) mbar_init(smem_u32(mbar_p + s), 1);
     fence_mbar_init();
   }
+  // every operand byte is finite from the start: zero-weight columns multiply whatever the neighbouring band holds
+  for (uint32_t o = tid * 16; o < S::O_BIAS; o += kThreads * 16) *reinterpret_cast<uint4*>(sm + o) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
   {
     const float* W0 = a.params + sh.w_off(0);
     const float* W1 = a.params + sh.w_off(1);
@@ -234,9 +264,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       *reinterpret_cast<__nv_bfloat16*>(sm + o_hi + off) = hi;
       *reinterpret_cast<__nv_bfloat16*>(sm + o_lo + off) = lo;
     };
-    for (int idx = tid; idx < 32 * DP; idx += kThreads) {  // T0[r = out][c = in] = W0[c][r]
-      const int r = idx / DP, c = idx % DP;
-      put(S::O_T0H, S::O_T0L, S::RG_T0, r, c, c < d ? W0[c * H + r] : 0.f);
+    for (int idx = tid; idx < 32 * S::KX; idx += kThreads) {  // T0X[r = out][c] = W0[c mod DP][r]  ([W0; W0])
+      const int r = idx / S::KX, c = idx % S::KX, ci = c % DP;
+      put(S::O_T0XH, S::O_T0XL, S::RG_T0X, r, c, ci < d ? W0[ci * H + r] : 0.f);
+    }
+    for (int idx = tid; idx < 32 * S::KV; idx += kThreads) {  // T0V[r = out][c = in] = W0[c][r], columns >= d zero
+      const int r = idx / S::KV, c = idx % S::KV;
+      put(S::O_T0VH, S::O_T0VL, S::RG_T0V, r, c, c < d ? W0[c * H + r] : 0.f);
     }
     for (int idx = tid; idx < 32 * 32; idx += kThreads) {
       const int r = idx / 32, c = idx % 32;
@@ -255,14 +289,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     if (a.tg.kind == PDEIP_DRIFT_LINEAR) ntg = d * d;
     else if (a.tg.kind == PDEIP_DRIFT_GMM) ntg = a.tg.n_gaussian * d;
     for (int i = tid; i < ntg; i += kThreads) tp[i] = a.tg.params[i];
-    // x|v|g tile: zero everything once, then the constant-one unit (column 3*DP) of every point
-    for (uint32_t o = tid * 16; o < S::SZ_X; o += kThreads * 16)
-      *reinterpret_cast<uint4*>(sm + S::O_X + o) = make_uint4(0, 0, 0, 0);
-  }
-  __syncthreads();
-  if (!is_mma_warp && sub == 0) {
-    float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    store_chunk(sm + S::O_X, chunk_off(row, 3 * DP / 8, S::RG_X), ones);
   }
   fence_async_smem();
   fence_before_sync();
@@ -270,703 +296,530 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
   fence_after_sync();
 
   const uint32_t TB = *tmem_p;
-  const uint32_t mb_fast = smem_u32(mbar_p), mb_dw = smem_u32(mbar_p + 1);
+  const int64_t tile_stride = (int64_t)gridDim.x * NS;
 
   // ==========================================================================================================
-  // MMA warp: one lane issues every tcgen05.mma of the tile in a fixed order, phase by phase
+  // MMA warp: one lane issues every tcgen05.mma, phase by phase, slot by slot
   // ==========================================================================================================
   if (is_mma_warp) {
-    const uint32_t xs = smem_u32(sm + S::O_X), a1s = smem_u32(sm + S::O_A1), a2s = smem_u32(sm + S::O_A2),
-                   zs = smem_u32(sm + S::O_Z);
-    // K-major views (rows = points / weight outputs): LBO = 128 (next 8 columns), SBO = row-group bytes
-    const uint64_t XK = make_desc(xs, 128, S::RG_X), A1K = make_desc(a1s, 128, S::RG_A),
-                   A2K = make_desc(a2s, 128, S::RG_A), ZK = make_desc(zs, 128, S::RG_Z);
-    const uint64_t T0HK = make_desc(smem_u32(sm + S::O_T0H), 128, S::RG_T0),
-                   T0LK = make_desc(smem_u32(sm + S::O_T0L), 128, S::RG_T0),
-                   T1HK = make_desc(smem_u32(sm + S::O_T1H), 128, S::RG_T1),
-                   T1LK = make_desc(smem_u32(sm + S::O_T1L), 128, S::RG_T1),
-                   T2HK = make_desc(smem_u32(sm + S::O_T2H), 128, S::RG_T2),
-                   T2LK = make_desc(smem_u32(sm + S::O_T2L), 128, S::RG_T2);
-    // transposed views (operand rows = tile columns): LBO = row-group bytes (next 8 tile rows), SBO = 128
-    const uint64_t XM = make_desc(xs, S::RG_X, 128), A1M = make_desc(a1s, S::RG_A, 128),
-                   A2M = make_desc(a2s, S::RG_A, 128), ZM = make_desc(zs, S::RG_Z, 128);
-    const uint64_t T0HM = make_desc(smem_u32(sm + S::O_T0H), S::RG_T0, 128),
-                   T0LM = make_desc(smem_u32(sm + S::O_T0L), S::RG_T0, 128),
-                   T1HM = make_desc(smem_u32(sm + S::O_T1H), S::RG_T1, 128),
-                   T1LM = make_desc(smem_u32(sm + S::O_T1L), S::RG_T1, 128),
-                   T2HM = make_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128),
-                   T2LM = make_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
-    constexpr uint32_t CB = 16;  // bytes per operand column inside a row of core matrices: 8 columns = 128 B
-    uint32_t not_first = 0;
+    // weights: K-major views (LBO = 128: next 8 columns, SBO = row-group bytes) and transposed views
+    const Desc T0XHK = mk_desc(smem_u32(sm + S::O_T0XH), 128, S::RG_T0X), T0XLK = mk_desc(smem_u32(sm + S::O_T0XL), 128, S::RG_T0X);
+    const Desc T0VHK = mk_desc(smem_u32(sm + S::O_T0VH), 128, S::RG_T0V), T0VLK = mk_desc(smem_u32(sm + S::O_T0VL), 128, S::RG_T0V);
+    const Desc T1HK = mk_desc(smem_u32(sm + S::O_T1H), 128, S::RG_T1), T1LK = mk_desc(smem_u32(sm + S::O_T1L), 128, S::RG_T1);
+    const Desc T2HK = mk_desc(smem_u32(sm + S::O_T2H), 128, S::RG_T2), T2LK = mk_desc(smem_u32(sm + S::O_T2L), 128, S::RG_T2);
+    const Desc T0VHM = mk_desc(smem_u32(sm + S::O_T0VH), S::RG_T0V, 128), T0VLM = mk_desc(smem_u32(sm + S::O_T0VL), S::RG_T0V, 128);
+    const Desc T1HM = mk_desc(smem_u32(sm + S::O_T1H), S::RG_T1, 128), T1LM = mk_desc(smem_u32(sm + S::O_T1L), S::RG_T1, 128);
+    const Desc T2HM = mk_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128), T2LM = mk_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
+    constexpr uint32_t CH = 128;  // bytes per chunk (8 operand columns)
+    uint32_t dw_started = 0;      // becomes 1 after the first tile's P3..P5 background GEMMs
 #pragma unroll 1
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-#ifdef PDEIP_TC_TRACE
-      long long* trace = reinterpret_cast<long long*>(status) + 8;
-      const bool trace_on = blockIdx.x == 0 && lane == 0 && tile == 100 * (int64_t)gridDim.x;
-      int ph = 0;
-#endif
-      // S0: z0 = x W0, z1_0 = v W0
-#ifdef PDEIP_TC_TRACE
-      ph = 0;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd<DP, 32>(TB + C_T1, XK, T0HK, T0LK);          // C_T1 and C_Z10 are not adjacent: two calls
-        mm_fwd<DP, 32>(TB + C_Z10, adv(XK, DP * CB), T0HK, T0LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
+    for (int64_t base = (int64_t)blockIdx.x * NS; base < n_tiles; base += tile_stride) {
+#pragma unroll 1
+      for (int ph = 0; ph < 12; ++ph) {
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+          const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
+          const uint32_t TS = TB + C_SLOT0 + (uint32_t)s * SLOT_COLS;
+          const uint32_t mb = smem_u32(mbar_p + s);
+          const Desc XK = mk_desc(sb + S::O_X, 128, S::RG_X), A1K = mk_desc(sb + S::O_A1, 128, S::RG_A),
+                     A2K = mk_desc(sb + S::O_A2, 128, S::RG_A), ZK = mk_desc(sb + S::O_Z, 128, S::RG_Z);
+          const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), A1M = mk_desc(sb + S::O_A1, S::RG_A, 128),
+                     A2M = mk_desc(sb + S::O_A2, S::RG_A, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
+          const uint32_t acc_first = (dw_started | (uint32_t)s) ? 1u : 0u;
+          mma_wait_operands(s);
+          if (elect_one()) {
+            switch (ph) {
+              case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
+                mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
+                mm_fwd<S::KV, 32, 1>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);
+                commit(mb);
+              } break;
+              case 1: {  // z1, z1_1, z2~_1
+                mm_fwd<32, 32, 3>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
+                commit(mb);
+              } break;
+              case 2: {  // u, u1, u2~
+                mm_fwd<32, OP, 3>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
+                commit(mb);
+              } break;
+              case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
+                mm_bwd<OP, 32, 2>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
+                commit(mb);
+                mm_outer<OP>(TB + C_DW2, A2M, AC_A1 * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+              } break;
+              case 4: {  // aa1 = za1 W1^T, ab1_1 = zbar1' W1^T;  dW1 += a1_1^T zbar1'
+                mm_bwd<32, 32, 2>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
+                commit(mb);
+                mm_outer<32>(TB + C_DW1, A1M, AC_A1 * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, acc_first);
+              } break;
+              case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
+                mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
+                commit(mb);
+                mm_outer<32>(TB + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+              } break;
+              case 6: {  // zg~_0 = g~ W0
+                mm_fwd<S::KV, 32, 1>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
+                commit(mb);
+              } break;
+              case 7: {  // zg~_1 = ag~_1 W1  (operand in the a1 band)
+                mm_fwd<32, 32, 1>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
+                commit(mb);
+              } break;
+              case 8: {  // ug~ = ag~_2 W2
+                mm_fwd<32, OP, 1>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
+                commit(mb);
+              } break;
+              case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
+                mm_bwd<OP, 32, 2>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                commit(mb);
+                mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+              } break;
+              case 10: {  // ab_1 = zbar0' W1^T, aa1 again;  dW1 += t1^T zbar0' + c_1^T za1
+                mm_bwd<32, 32, 2>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                commit(mb);
+                mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
+                mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+              } break;
+              default: {  // dW0 += x_hi^T zbar0'' + x_lo^T zbar0'' + g~^T za0
+                mm_outer<32>(TB + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                mm_outer<32>(TB + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                commit(mb);  // the next tile's E0 overwrites the x | v bands
+              } break;
+            }
+          }
+          __syncwarp();
+        }
       }
-      // S1: z1, z1_1, z2_1
-#ifdef PDEIP_TC_TRACE
-      ph = 1;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd<32, 32>(TB + C_T2, A1K, T1HK, T1LK);
-        mm_fwd_multi<32, 32, 2>(TB + C_Z11, 32, adv(A1K, 32 * CB), 32 * CB, T1HK, T1LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S2: u, u1, u2
-#ifdef PDEIP_TC_TRACE
-      ph = 2;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd_multi<32, OP, 3>(TB + C_U, OP, A2K, 32 * CB, T2HK, T2LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S3: aa_2 = za_2 W2^T
-#ifdef PDEIP_TC_TRACE
-      ph = 3;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_bwd<OP, 32>(TB + C_AA2, ZK, T2HM, T2LM, S::RG_T2);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S4: aa_1 = za_1 W1^T
-#ifdef PDEIP_TC_TRACE
-      ph = 4;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_bwd<32, 32>(TB + C_AA1, adv(ZK, OP * CB), T1HM, T1LM, S::RG_T1);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S5: g = za_0 W0^T
-#ifdef PDEIP_TC_TRACE
-      ph = 5;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_bwd<32, DP>(TB + C_G, adv(ZK, 2 * OP * CB), T0HM, T0LM, S::RG_T0);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S6: zg_0 = g W0
-#ifdef PDEIP_TC_TRACE
-      ph = 6;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd<DP, 32>(TB + C_ZG0, adv(XK, 2 * DP * CB), T0HK, T0LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S7: zg_1 = ag_1 W1
-#ifdef PDEIP_TC_TRACE
-      ph = 7;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd<32, 32>(TB + C_ZG1, adv(A1K, 96 * CB), T1HK, T1LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S8: ug = ag_2 W2
-#ifdef PDEIP_TC_TRACE
-      ph = 8;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_fwd<32, OP>(TB + C_UG, adv(A2K, 96 * CB), T2HK, T2LK);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-      }
-      // S9: abar_s = Ubar_s W2^T (fast);  dW2_s = ACT2^T Ubar_s, db2 (background)
-#ifdef PDEIP_TC_TRACE
-      ph = 9;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) mm_bwd<OP, 32>(TB + C_AB + 32 * s, adv(ZK, OP * s * CB), T2HM, T2LM, S::RG_T2);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) mm_outer<OP>(TB + C_DW + OP * s, A2M, S::RG_A, adv(ZM, OP * s * CB), S::RG_Z, 0);
-        mm_outer<OP>(TB + C_DB2, XM, S::RG_X, ZM, S::RG_Z, not_first);
-        commit(mb_dw);
-      }
-      // S10: abar'_s = zbar_s W1^T (fast);  dW1_s = ACT1^T zbar_s, db1 (background)
-#ifdef PDEIP_TC_TRACE
-      ph = 10;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) mm_bwd<32, 32>(TB + C_AB + 32 * s, adv(ZK, OP * s * CB), T1HM, T1LM, S::RG_T1);
-        commit(mb_fast);
-        TC_TRACE(2, ph);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) mm_outer<32>(TB + C_DW + 32 * s, A1M, S::RG_A, adv(ZM, OP * s * CB), S::RG_Z, 0);
-        mm_outer<32>(TB + C_DB1, XM, S::RG_X, ZM, S::RG_Z, not_first);
-        commit(mb_dw);
-      }
-      // S11: dW0 regions: rows x <-> zbar', rows v <-> zbar1', rows g <-> zbar_g'
-#ifdef PDEIP_TC_TRACE
-      ph = 11;
-#endif
-      mma_wait_operands();
-      TC_TRACE(1, ph);
-      if (elect_one()) {
-        mm_outer_multi<32, 3>(TB + C_DW, 32, XM, S::RG_X, ZM, OP * CB, S::RG_Z);
-        commit(mb_dw);
-      }
-      not_first = 1;
+      dw_started = 1u;
     }
   } else {
     // ========================================================================================================
     // epilogue warps
     // ========================================================================================================
-    Ctx c;
-    c.tbase = TB;
-    c.lane_addr = TB + ((uint32_t)(q * 32) << 16);
-    c.mb_fast = mb_fast;
-    c.mb_dw = mb_dw;
-    c.par_fast = 0;
-    c.par_dw = 0;
-    c.status = status;
-    c.ok = true;
-    const uint32_t LA = c.lane_addr;
-    uint8_t* X = sm + S::O_X;
-    uint8_t* A1 = sm + S::O_A1;
-    uint8_t* A2 = sm + S::O_A2;
-    uint8_t* Z = sm + S::O_Z;
-    auto ST = [&](int arr, int unit) -> float& { return stash[(arr * 32 + unit) * 128 + row]; };
-
-    // running sums kept in registers across the CTA's tiles (this thread's chunk of the rows its lane owns)
-    float acc2[16], acc1[8], acc0[8];
+    int* const status_w = status;
+    bool ok = true;
+    uint32_t par[NS];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+    for (int s = 0; s < NS; ++s) par[s] = 0;
+#ifdef PDEIP_TC_PROBE
+    float* probe = reinterpret_cast<float*>(status) + 64;
+#endif
+    // bias-gradient sums over this thread's row (chunk `sub` of the hidden layers; chunks sub, sub + 4 of the output)
+    float db0a[8], db1a[8], db2a[8], db2b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc1[j] = 0.f; acc0[j] = 0.f; }
-    float sums[PDEIP_NUM_SUMS];
-#pragma unroll
-    for (int k = 0; k < PDEIP_NUM_SUMS; ++k) sums[k] = 0.f;
+    for (int i = 0; i < 8; ++i) { db0a[i] = 0.f; db1a[i] = 0.f; db2a[i] = 0.f; db2b[i] = 0.f; }
+    float sum_g2 = 0.f, sum_gt2 = 0.f, sum_gd2 = 0.f, sum_d1 = 0.f, sum_d2 = 0.f;
     const float gamma = a.coef;
-    const int cg4 = sub;  // the chunk of a 32-unit tile owned by this thread
-    // this thread's x|v input chunk (sub-warps with sub < 2*DP/8 own one), prefetched one tile ahead
     const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
-    const bool has_in = sub < 2 * (DP / 8);
-    const int in_band = sub / (DP / 8), in_cg = sub % (DP / 8);
-    float xin[8];
-    auto load_inputs = [&](int64_t t) {
-      const int64_t pp = t * 128 + row;
-      const bool ok_p = has_in && t < n_tiles && pp < a.n_points;
+    // prefetched input chunks: item j = sub + 4 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
+    float xin[NS][S::NI][8];
+    auto load_inputs = [&](int s, int64_t t) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int u = in_cg * 8 + i;
-        xin[i] = (ok_p && u < d) ? __ldg(a.points + elem_index(a.layout, pp, in_band * d + u, a.n_points, dimw)) : 0.f;
+      for (int i = 0; i < S::NI; ++i) {
+        const int j = sub + 4 * i;
+        const int band = j / S::XC, cg = j % S::XC;
+        const int64_t pp = t * 128 + row;
+        const bool ok_p = j < 3 * S::XC && t < n_tiles && pp < a.n_points && (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int u = cg * 8 + e;
+          xin[s][i][e] = (ok_p && u < d) ? __ldg(a.points + elem_index(a.layout, pp, band * d + u, a.n_points, dimw)) : 0.f;
+        }
       }
     };
-    load_inputs(blockIdx.x);
-#ifdef PDEIP_TC_TRACE
-    if (blockIdx.x == 0 && tid == 0) (reinterpret_cast<long long*>(status) + 8)[62] = clock64();
-#endif
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_inputs(s, (int64_t)blockIdx.x * NS + s);
 
+    bool first = true;
 #pragma unroll 1
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t p = tile * 128 + row;
-      const bool valid = p < a.n_points;
-      const float wt = valid ? a.weight : 0.f;
-      const float alpha = -2.f * wt, beta = 2.f * gamma * wt, beta_g = 2.f * wt;
-#ifdef PDEIP_TC_TRACE
-      long long* trace = reinterpret_cast<long long*>(status) + 8;
-      const bool trace_on = blockIdx.x == 0 && tid == 0 && tile == 100 * (int64_t)gridDim.x;
-      if (trace_on) trace[60] = clock64();
-      int eph = 0;
-#endif
-      // ---- S0: x, v bands (one prefetched chunk per sub-warp; DP = 16: x0 x1 v0 v1) -----------------------
-      static_assert(2 * (DP / 8) <= 4, "one input chunk per sub-warp");
-      if (has_in) store_chunk(X, chunk_off(row, in_band * (DP / 8) + in_cg, S::RG_X), xin);
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S1: t1, a1_1, a2_1 -------------------------------------------------------------------------
-      {
-        float z0[8], z1[8], t[8], q1[8], q2[8];
-        tmem_ld8x2(LA + C_T1 + 8 * cg4, LA + C_Z10 + 8 * cg4, z0, z1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          t[i] = tanh_fast(z0[i] + bias_s[cg4 * 8 + i]);
-          const float s1 = 1.f - t[i] * t[i];
-          q1[i] = s1 * z1[i];
-          q2[i] = (-2.f * t[i] * s1) * z1[i] * z1[i];
-          ST(ST_Z10, cg4 * 8 + i) = z1[i];
-        }
-        store_chunk(A1, chunk_off(row, cg4, S::RG_A), t);
-        store_chunk(A1, chunk_off(row, 4 + cg4, S::RG_A), q1);
-        store_chunk(A1, chunk_off(row, 8 + cg4, S::RG_A), q2);
-        tmem_st8(LA + C_T1 + 8 * cg4, t);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S2: t2, a1_2, a2_2 -------------------------------------------------------------------------
-      {
-        float z0[8], z1[8], z2[8], t[8], q1[8], q2[8];
-        tmem_ld8x3(LA + C_T2 + 8 * cg4, LA + C_Z11 + 8 * cg4, LA + C_Z21 + 8 * cg4, z0, z1, z2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          t[i] = tanh_fast(z0[i] + bias_s[32 + cg4 * 8 + i]);
-          const float s1 = 1.f - t[i] * t[i];
-          q1[i] = s1 * z1[i];
-          q2[i] = s1 * z2[i] + (-2.f * t[i] * s1) * z1[i] * z1[i];
-          ST(ST_Z11, cg4 * 8 + i) = z1[i];
-          ST(ST_Z21, cg4 * 8 + i) = z2[i];
-        }
-        store_chunk(A2, chunk_off(row, cg4, S::RG_A), t);
-        store_chunk(A2, chunk_off(row, 4 + cg4, S::RG_A), q1);
-        store_chunk(A2, chunk_off(row, 8 + cg4, S::RG_A), q2);
-        tmem_st8(LA + C_T2 + 8 * cg4, t);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S3: za_2 = 2u  ->  aa_2 = za_2 W2^T ---------------------------------------------------------
+    for (int64_t base = (int64_t)blockIdx.x * NS; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
-      for (int cg = sub; cg < OP / 8; cg += 4) {
-        float u[8];
-        tmem_ld8(LA + C_U + 8 * cg, u);
+      for (int ph = 0; ph < 12; ++ph) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = 2.f * (u[i] + bias_s[64 + cg * 8 + i]);
-        store_chunk(Z, chunk_off(row, cg, S::RG_Z), u);
-      }
-      if (a.tg.kind == PDEIP_DRIFT_GMM) {
-        // true gradient of the GMM potential (core/potential.py:32-37), centres k = sub, sub+4, ... handled by this
-        // sub-warp with an online softmax; the partial (m, se, sum e mu) goes to free TMEM columns of this lane and is
-        // combined by sub-warp 0 in S6
-        float x[DP];
-#pragma unroll
-        for (int u = 0; u < DP; ++u)
-          x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
-        float m = -INFINITY, se = 0.f, accg[DP];
-#pragma unroll
-        for (int u = 0; u < DP; ++u) accg[u] = 0.f;
-        for (int k = sub; k < a.tg.n_gaussian; k += 4) {
-          const float* mu = tp + k * d;
-          float s2 = 0.f;
-#pragma unroll
-          for (int u = 0; u < DP; ++u)
-            if (u < d) {
-              const float r = x[u] - mu[u];
-              s2 = fmaf(r, r, s2);
+        for (int s = 0; s < NS; ++s) {
+          uint8_t* const X = sm + (uint32_t)s * S::SLOT + S::O_X;
+          uint8_t* const A1 = sm + (uint32_t)s * S::SLOT + S::O_A1;
+          uint8_t* const A2 = sm + (uint32_t)s * S::SLOT + S::O_A2;
+          uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z;
+          const uint32_t LA = TB + ((uint32_t)(q * 32) << 16) + C_SLOT0 + (uint32_t)s * SLOT_COLS;
+          const int64_t tile = base + s;
+          const int64_t p = tile * 128 + row;
+          const bool valid = tile < n_tiles && p < a.n_points;
+          const float mk = valid ? 1.f : 0.f;
+#ifdef PDEIP_TC_PROBE
+          const bool probe_on = blockIdx.x == 0 && tile == 0;
+#endif
+          // wait for the GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
+          if (!(first && ph == 0)) {
+            if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
+              ok = false;
+              atomicExch(status_w, 1);
             }
-          const float ak = -0.5f * a.tg.inv_sigma2 * s2;
-          if (ak > m) {
-            const float sc = __expf(m - ak);
-            se *= sc;
-#pragma unroll
-            for (int u = 0; u < DP; ++u) accg[u] *= sc;
-            m = ak;
+            par[s] ^= 1u;
+            fence_after_sync();
           }
-          const float e = __expf(ak - m);
-          se += e;
+          switch (ph) {
+            case 0: {  // E0: x (hi + lo) and v bands of this tile; prefetch registers are refilled in E1
 #pragma unroll
-          for (int u = 0; u < DP; ++u)
-            if (u < d) accg[u] = fmaf(e, mu[u], accg[u]);
-        }
+              for (int i = 0; i < S::NI; ++i) {
+                const int j = sub + 4 * i;
+                const int band = j / S::XC, cg = j % S::XC;
+                if (band == 0) {
+                  float hi[8], lo[8];
 #pragma unroll
-        for (int cg = 0; cg < DP / 8; ++cg) {
-          float w8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w8[i] = accg[cg * 8 + i];
-          tmem_st8(LA + C_GX + DP * sub + 8 * cg, w8);
-        }
-        tmem_st2(LA + C_GMS + 2 * sub, m, se);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S4: za_1 = aa_2 (1 - t2^2) -> aa_1 ----------------------------------------------------------
-      {
-        float aa[8], t[8];
-        tmem_ld8x2(LA + C_AA2 + 8 * cg4, LA + C_T2 + 8 * cg4, aa, t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) aa[i] *= (1.f - t[i] * t[i]);
-        store_chunk(Z, chunk_off(row, OP / 8 + cg4, S::RG_Z), aa);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S5: za_0 = aa_1 (1 - t1^2) -> g -------------------------------------------------------------
-      {
-        float aa[8], t[8];
-        tmem_ld8x2(LA + C_AA1 + 8 * cg4, LA + C_T1 + 8 * cg4, aa, t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) aa[i] *= (1.f - t[i] * t[i]);
-        store_chunk(Z, chunk_off(row, 2 * OP / 8 + cg4, S::RG_Z), aa);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S6: g band; |g|^2 and the true gradient (sub-warp 0 sees the whole point) ------------------------
-#pragma unroll 1
-      for (int cg = sub; cg < DP / 8; cg += 4) {
-        float gv[8];
-        tmem_ld8(LA + C_G + 8 * cg, gv);
-        store_chunk(X, chunk_off(row, 2 * DP / 8 + cg, S::RG_X), gv);
-      }
-      {
-        // every sub-warp sees x and g; rows i = sub, sub+4, ... of the true gradient are handled here (all loss terms
-        // are sums over i, so no exchange is needed); the GMM softmax partials of S3 are combined first
-        float x[DP], gq[DP];
-#pragma unroll
-        for (int cg = 0; cg < DP / 8; ++cg) {
-          float gv[8];
-          tmem_ld8(LA + C_G + 8 * cg, gv);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gq[cg * 8 + i] = gv[i];
-        }
-        if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
-#pragma unroll
-          for (int u = 0; u < DP; ++u)
-            x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
-        }
-        float g2 = 0.f, gt2 = 0.f, gd2 = 0.f;
-        if (a.tg.kind == PDEIP_DRIFT_GMM) {
-          float ms[8];
-          tmem_ld8(LA + C_GMS, ms);  // (m, se) of the four sub-warps
-          float m = fmaxf(fmaxf(ms[0], ms[2]), fmaxf(ms[4], ms[6]));
-          float sc[4], se = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sc[j] = (ms[2 * j + 1] > 0.f) ? __expf(ms[2 * j] - m) : 0.f;  // a sub-warp without centres has se = 0
-            se = fmaf(sc[j], ms[2 * j + 1], se);
-          }
-          const float inv = 1.f / se;
-#pragma unroll
-          for (int cg = 0; cg < DP / 8; ++cg) {
-            float p0[8], p1[8], p2[8], p3[8];
-            tmem_ld8x4(LA + C_GX + 8 * cg, LA + C_GX + DP + 8 * cg, LA + C_GX + 2 * DP + 8 * cg,
-                       LA + C_GX + 3 * DP + 8 * cg, p0, p1, p2, p3);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int u = cg * 8 + i;
-              if ((u & 3) == sub && u < d) {
-                const float wmu = (sc[0] * p0[i] + sc[1] * p1[i]) + (sc[2] * p2[i] + sc[3] * p3[i]);
-                const float gti = (x[u] - wmu * inv) * a.tg.inv_sigma2;
-                g2 = fmaf(gq[u], gq[u], g2);
-                gt2 = fmaf(gti, gti, gt2);
-                gd2 = fmaf(gti - gq[u], gti - gq[u], gd2);
+                  for (int e = 0; e < 8; ++e) {
+                    hi[e] = __bfloat162float(__float2bfloat16_rn(xin[s][i][e]));
+                    lo[e] = xin[s][i][e] - hi[e];
+                  }
+                  store_chunk(X, chunk_off(row, S::XC_HI + cg, S::RG_X), hi);
+                  store_chunk(X, chunk_off(row, S::XC_LO + cg, S::RG_X), lo);
+                } else if (band == 1) {
+                  store_chunk(X, chunk_off(row, S::XC_V + cg, S::RG_X), xin[s][i]);
+                }
               }
-            }
-          }
-        } else {
+            } break;
+            case 1: {  // E1: t1, a1_1, a2~_1 = 4 t a1 z1
+              float z0[8], z1[8], t[8], s1[8], q1[8], q2[8];
+              tmem_ld8x2(LA + C_Z0 + 8 * sub, LA + C_Z10 + 8 * sub, z0, z1);
 #pragma unroll
-          for (int u = 0; u < DP; ++u) {
-            if ((u & 3) == sub && u < d) {
-              float gti = 0.f;
-              if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {  // stored next to the point by the integrator
-                gti = valid ? __ldg(a.points + elem_index(a.layout, p, 2 * d + u, a.n_points, dimw)) : 0.f;
-              } else if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
-#pragma unroll
-                for (int k = 0; k < DP; ++k)
-                  if (k < d) gti = fmaf(tp[u * d + k], x[k], gti);
+              for (int i = 0; i < 8; ++i) {
+                t[i] = tanh_fast(z0[i] + bias_s[sub * 8 + i]);
+                s1[i] = 1.f - t[i] * t[i];
+                q1[i] = s1[i] * z1[i];
+                q2[i] = 4.f * t[i] * q1[i] * z1[i];
               }
-              g2 = fmaf(gq[u], gq[u], g2);
-              gt2 = fmaf(gti, gti, gt2);
-              gd2 = fmaf(gti - gq[u], gti - gq[u], gd2);
-            }
-          }
-        }
-        sums[PDEIP_SUM_G2] += wt * g2;
-        sums[PDEIP_SUM_GTRUE2] += wt * gt2;
-        sums[PDEIP_SUM_GT] += wt * gd2;
-        sums[PDEIP_SUM_LOSS] += wt * (g2 + gt2);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S7: ag_1 = (1 - t1^2) zg_0 ------------------------------------------------------------------
-      {
-        float zg[8], t[8];
-        tmem_ld8x2(LA + C_ZG0 + 8 * cg4, LA + C_T1 + 8 * cg4, zg, t);
+              store_chunk(A1, chunk_off(row, AC_T + sub, S::RG_A), t);
+              store_chunk(A1, chunk_off(row, AC_A1 + sub, S::RG_A), q1);
+              store_chunk(A1, chunk_off(row, AC_C + sub, S::RG_A), q2);
+              tmem_park8(LA + C_S1P1 + 4 * sub, s1);
+              TC_PROBE(0, sub * 8, t);
+              TC_PROBE(1, sub * 8, q1);
+              TC_PROBE(2, sub * 8, q2);
+            } break;
+            case 2: {  // E2: t2, a1_2, a2~_2 = s1 z2~ + 4 t a1 z1
+              float z0[8], z1[8], z2[8], t[8], s1[8], q1[8], q2[8];
+              tmem_ld8x3(LA + C_Z1 + 8 * sub, LA + C_Z11 + 8 * sub, LA + C_Z21 + 8 * sub, z0, z1, z2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ST(ST_ZG0, cg4 * 8 + i) = zg[i];
-          zg[i] *= (1.f - t[i] * t[i]);
-        }
-        store_chunk(A1, chunk_off(row, 12 + cg4, S::RG_A), zg);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S8: ag_2 = (1 - t2^2) zg_1 ------------------------------------------------------------------
-      {
-        float zg[8], t[8];
-        tmem_ld8x2(LA + C_ZG1 + 8 * cg4, LA + C_T2 + 8 * cg4, zg, t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ST(ST_ZG1, cg4 * 8 + i) = zg[i];
-          zg[i] *= (1.f - t[i] * t[i]);
-        }
-        store_chunk(A2, chunk_off(row, 12 + cg4, S::RG_A), zg);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S9: loss terms and seeds ----------------------------------------------------------
-      {
-        float d1 = 0.f, d2a = 0.f, d2b = 0.f;
+              for (int i = 0; i < 8; ++i) {
+                t[i] = tanh_fast(z0[i] + bias_s[32 + sub * 8 + i]);
+                s1[i] = 1.f - t[i] * t[i];
+                q1[i] = s1[i] * z1[i];
+                q2[i] = fmaf(s1[i], z2[i], 4.f * t[i] * q1[i] * z1[i]);
+              }
+              store_chunk(A2, chunk_off(row, AC_T + sub, S::RG_A), t);
+              store_chunk(A2, chunk_off(row, AC_A1 + sub, S::RG_A), q1);
+              store_chunk(A2, chunk_off(row, AC_C + sub, S::RG_A), q2);
+              tmem_park8(LA + C_S1P2 + 4 * sub, s1);
+              TC_PROBE(3, sub * 8, t);
+              TC_PROBE(4, sub * 8, q1);
+              TC_PROBE(5, sub * 8, q2);
+            } break;
+            case 3: {  // E3: za2 = 2u, s1v, s0p, D_v V, D_v^2 V
+              float d1 = 0.f, d2a = 0.f, d2b = 0.f;
 #pragma unroll 1
-        for (int cg = sub; cg < OP / 8; cg += 4) {
-          float u[8], u1[8], u2[8], ug[8], s0[8], s1v[8], s2v[8], sg[8];
-          tmem_ld8x4(LA + C_U + 8 * cg, LA + C_U1 + 8 * cg, LA + C_U2 + 8 * cg, LA + C_UG + 8 * cg, u, u1, u2, ug);
+              for (int cg = sub; cg < OP / 8; cg += 4) {
+                float u[8], u1[8], u2[8], za[8], sv[8], sp[8];
+                tmem_ld8x3(LA + C_U + 8 * cg, LA + C_U1 + 8 * cg, LA + C_U2 + 8 * cg, u, u1, u2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float uu = u[i] + bias_s[64 + cg * 8 + i];
-            d1 = fmaf(uu, u1[i], d1);
-            d2a = fmaf(u1[i], u1[i], d2a);
-            d2b = fmaf(uu, u2[i], d2b);
-            s0[i] = 2.f * alpha * u2[i] + 2.f * beta * u1[i] + 2.f * beta_g * ug[i];
-            s1v[i] = 4.f * alpha * u1[i] + 2.f * beta * uu;
-            s2v[i] = 2.f * alpha * uu;
-            sg[i] = 2.f * beta_g * uu;
+                for (int i = 0; i < 8; ++i) {
+                  const float uu = u[i] + bias_s[64 + cg * 8 + i];
+                  d1 = fmaf(uu, u1[i], d1);
+                  d2a = fmaf(u1[i], u1[i], d2a);
+                  d2b = fmaf(uu, u2[i], d2b);
+                  za[i] = 2.f * mk * uu;
+                  sv[i] = mk * fmaf(-8.f, u1[i], 4.f * gamma * uu);
+                  sp[i] = mk * fmaf(2.f, u2[i], 4.f * gamma * u1[i]);
+                }
+                store_chunk(Z, chunk_off(row, ZC_ZA2 + cg, S::RG_Z), za);
+                store_chunk(Z, chunk_off(row, ZC_TA + cg, S::RG_Z), sv);
+                tmem_park8(LA + C_S0P + 4 * cg, sp);
+                TC_PROBE(6, cg * 8, za);
+                TC_PROBE(7, cg * 8, sv);
+                TC_PROBE(8, cg * 8, sp);
+              }
+              // this thread's share of D_v V = 2 u.u1 and D_v^2 V = 2 (u1.u1 + u.u2), u2 = -u2~ / 2
+              sum_d1 += mk * 2.f * d1;
+              sum_d2 += mk * (2.f * d2a - d2b);
+            } break;
+            case 4:    // E4: za1, zbar1', pz2  (hidden layer 2)
+            case 5: {  // E5: za0, zbar1'', pz1 (hidden layer 1)
+              const bool l2 = ph == 4;
+              const uint8_t* At = l2 ? A2 : A1;
+              float aa[8], ab1[8], s1[8], t[8], a1[8], za[8], zb[8], pz[8];
+              uint4 s1q;
+              tmem_ld8_raw(LA + (l2 ? C_AA2 : C_AA1) + 8 * sub, aa);
+              tmem_ld8_raw(LA + (l2 ? C_AB12 : C_AB11) + 8 * sub, ab1);
+              tmem_ld4_raw(LA + (l2 ? C_S1P2 : C_S1P1) + 4 * sub, s1q);
+              load_chunk(At, chunk_off(row, AC_T + sub, S::RG_A), t);
+              load_chunk(At, chunk_off(row, AC_A1 + sub, S::RG_A), a1);
+              tmem_wait_ld();
+              unpack8(s1q, s1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                za[i] = aa[i] * s1[i];
+                const float qq = aa[i] * a1[i];
+                zb[i] = fmaf(s1[i], ab1[i], 8.f * t[i] * qq);
+                pz[i] = fmaf(-2.f * t[i] * ab1[i], a1[i], 4.f * qq * a1[i]);
+              }
+              store_chunk(Z, chunk_off(row, (l2 ? ZC_ZA1 : ZC_ZA0) + sub, S::RG_Z), za);
+              store_chunk(Z, chunk_off(row, (l2 ? ZC_TB : ZC_TA) + sub, S::RG_Z), zb);
+              tmem_park8(LA + (l2 ? C_PZ2 : C_PZ1) + 4 * sub, pz);
+              TC_PROBE(l2 ? 9 : 12, sub * 8, za);
+              TC_PROBE(l2 ? 10 : 13, sub * 8, zb);
+              TC_PROBE(l2 ? 11 : 14, sub * 8, pz);
+            } break;
+            case 6: {  // E6: g~ = 2 g band; |g|^2, |g_true|^2, |g_true - g|^2
+              // item j of this thread: band 2 (stored true gradient) chunks own the sums when the gradient is stored;
+              // otherwise the x-chunk owners do (they hold x for the inline true gradient)
+#pragma unroll
+              for (int i = 0; i < S::NI; ++i) {
+                const int j = sub + 4 * i;
+                const int band = j / S::XC, cg = j % S::XC;
+                if (j < 3 * S::XC && band == 0) {  // writes the g~ chunk
+                  float gv[8], g2v[8];
+                  tmem_ld8(LA + C_G + 8 * cg, gv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) g2v[e] = 2.f * gv[e];
+                  store_chunk(X, chunk_off(row, S::XC_G + cg, S::RG_X), g2v);
+                  TC_PROBE(15, cg * 8, gv);
+                  if (a.tg.kind != PDEIP_DRIFT_IN_POINTS) {
+                    float gt[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gt[e] = 0.f;
+                    if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
+                      float x[DP];
+#pragma unroll
+                      for (int u = 0; u < DP; ++u)
+                        x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
+                      if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                          const int u = cg * 8 + e;
+                          if (u < d) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int k = 0; k < DP; ++k)
+                              if (k < d) acc = fmaf(tp[u * d + k], x[k], acc);
+                            gt[e] = acc;
+                          }
+                        }
+                      } else {
+                        float m = -INFINITY;
+                        for (int k = 0; k < a.tg.n_gaussian; ++k) {
+                          float s2 = 0.f;
+#pragma unroll
+                          for (int u = 0; u < DP; ++u)
+                            if (u < d) {
+                              const float r = x[u] - tp[k * d + u];
+                              s2 = fmaf(r, r, s2);
+                            }
+                          m = fmaxf(m, -0.5f * a.tg.inv_sigma2 * s2);
+                        }
+                        float se = 0.f, wm[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) wm[e] = 0.f;
+                        for (int k = 0; k < a.tg.n_gaussian; ++k) {
+                          float s2 = 0.f;
+#pragma unroll
+                          for (int u = 0; u < DP; ++u)
+                            if (u < d) {
+                              const float r = x[u] - tp[k * d + u];
+                              s2 = fmaf(r, r, s2);
+                            }
+                          const float ek = __expf(-0.5f * a.tg.inv_sigma2 * s2 - m);
+                          se += ek;
+#pragma unroll
+                          for (int e = 0; e < 8; ++e)
+                            if (cg * 8 + e < d) wm[e] = fmaf(ek, tp[k * d + cg * 8 + e], wm[e]);
+                        }
+                        const float inv = 1.f / se;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                          if (cg * 8 + e < d) gt[e] = (x[cg * 8 + e] - wm[e] * inv) * a.tg.inv_sigma2;
+                      }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
+                      sum_gt2 = fmaf(mk * gt[e], gt[e], sum_gt2);
+                      sum_gd2 = fmaf(mk * (gt[e] - gv[e]), gt[e] - gv[e], sum_gd2);
+                    }
+                  }
+                } else if (j < 3 * S::XC && band == 2 && a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+                  float gv[8];
+                  tmem_ld8(LA + C_G + 8 * cg, gv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float gt = xin[s][i][e];
+                    sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
+                    sum_gt2 = fmaf(mk * gt, gt, sum_gt2);
+                    sum_gd2 = fmaf(mk * (gt - gv[e]), gt - gv[e], sum_gd2);
+                  }
+                }
+              }
+            } break;
+            case 7:    // E7: ag~_1 = s1_1 zg~_0 -> a1 band of A1;  c_1 = a2~_1 + ag~_1
+            case 8: {  // E8: ag~_2 = s1_2 zg~_1 -> a1 band of A2;  c_2
+              const bool l1 = ph == 7;
+              uint8_t* At = l1 ? A1 : A2;
+              float zg[8], s1[8], a2[8], ag[8], c[8];
+              uint4 s1q;
+              tmem_ld8_raw(LA + (l1 ? C_ZG0 : C_ZG1) + 8 * sub, zg);
+              tmem_ld4_raw(LA + (l1 ? C_S1P1 : C_S1P2) + 4 * sub, s1q);
+              load_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), a2);
+              tmem_wait_ld();
+              unpack8(s1q, s1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                ag[i] = s1[i] * zg[i];
+                c[i] = a2[i] + ag[i];
+              }
+              store_chunk(At, chunk_off(row, AC_A1 + sub, S::RG_A), ag);
+              store_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), c);
+              TC_PROBE(l1 ? 16 : 17, sub * 8, c);
+            } break;
+            case 9: {  // E9: s0 = s0p + 2 ug~;  db2 += s0
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int cg = sub + 4 * h;
+                if (cg < OP / 8) {
+                  float ug[8], sp[8], s0[8];
+                  uint4 spq;
+                  tmem_ld8_raw(LA + C_UG + 8 * cg, ug);
+                  tmem_ld4_raw(LA + C_S0P + 4 * cg, spq);
+                  tmem_wait_ld();
+                  unpack8(spq, sp);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    s0[i] = fmaf(2.f, ug[i], sp[i]);
+                    if (h == 0) db2a[i] += s0[i];
+                    else db2b[i] += s0[i];
+                  }
+                  store_chunk(Z, chunk_off(row, ZC_TA + cg, S::RG_Z), s0);
+                  TC_PROBE(18, cg * 8, s0);
+                }
+              }
+            } break;
+            case 10:    // E10: zbar0' = s1_2 ab_2 + pz2 - 2 t2 aa2 c_2;  db1
+            default: {  // E11: zbar0'' = s1_1 ab_1 + pz1 - 2 t1 aa1 c_1;  db0
+              const bool l2 = ph == 10;
+              const uint8_t* At = l2 ? A2 : A1;
+              float ab[8], aa[8], s1[8], pz[8], t[8], c[8], zb[8];
+              uint4 s1q, pzq;
+              tmem_ld8_raw(LA + (l2 ? C_AB2 : C_AB1) + 8 * sub, ab);
+              tmem_ld8_raw(LA + (l2 ? C_AA2R : C_AA1R) + 8 * sub, aa);
+              tmem_ld4_raw(LA + (l2 ? C_S1P2 : C_S1P1) + 4 * sub, s1q);
+              tmem_ld4_raw(LA + (l2 ? C_PZ2 : C_PZ1) + 4 * sub, pzq);
+              load_chunk(At, chunk_off(row, AC_T + sub, S::RG_A), t);
+              load_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), c);
+              tmem_wait_ld();
+              unpack8(s1q, s1);
+              unpack8(pzq, pz);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                zb[i] = fmaf(s1[i], ab[i], fmaf(-2.f * t[i] * aa[i], c[i], pz[i]));
+                if (l2) db1a[i] += zb[i];
+                else db0a[i] += zb[i];
+              }
+              store_chunk(Z, chunk_off(row, (l2 ? ZC_TB : ZC_TA) + sub, S::RG_Z), zb);
+              TC_PROBE(l2 ? 19 : 20, sub * 8, zb);
+              // prefetch the next tile of this slot while its last GEMMs run
+              if (!l2) load_inputs(s, tile + tile_stride);
+            } break;
           }
-          store_chunk(Z, chunk_off(row, cg, S::RG_Z), s0);
-          store_chunk(Z, chunk_off(row, OP / 8 + cg, S::RG_Z), s1v);
-          store_chunk(Z, chunk_off(row, 2 * OP / 8 + cg, S::RG_Z), s2v);
-          store_chunk(Z, chunk_off(row, 3 * OP / 8 + cg, S::RG_Z), sg);
-        }
-        // this thread's share (its chunks) of D_v V = 2 u.u1 and D_v^2 V = 2 (u1.u1 + u.u2); all terms are linear
-        const float D1 = 2.f * d1, D2 = 2.f * (d2a + d2b);
-        sums[PDEIP_SUM_D2] += wt * D2;
-        sums[PDEIP_SUM_D1] += wt * D1;
-        sums[PDEIP_SUM_LOSS] += wt * (-2.f * D2 + 2.f * gamma * D1);
-      }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S10: through tanh of hidden layer 2 (while the dW2 GEMMs run), then store zbar, read dW2 ----------
-      {
-        float ab[8], ab1[8], ab2[8], abg[8], t[8];
-        tmem_ld8x4(LA + C_AB + 8 * cg4, LA + C_AB + 32 + 8 * cg4, LA + C_AB + 64 + 8 * cg4, LA + C_AB + 96 + 8 * cg4,
-                   ab, ab1, ab2, abg);
-        tmem_ld8(LA + C_T2 + 8 * cg4, t);
-        float o0[8], o1[8], o2[8], og[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int un = cg4 * 8 + i;
-          const float tt = t[i], s1 = 1.f - tt * tt, s2 = -2.f * tt * s1;
-          const float z1 = ST(ST_Z11, un), z2 = ST(ST_Z21, un), zg = ST(ST_ZG1, un);
-          const float tb = ab[i] + ab1[i] * z1 * (-2.f * tt) +
-                           ab2[i] * (z2 * (-2.f * tt) + z1 * z1 * (6.f * tt * tt - 2.f)) + abg[i] * zg * (-2.f * tt);
-          o0[i] = tb * s1;
-          o1[i] = ab1[i] * s1 + ab2[i] * 2.f * s2 * z1;
-          o2[i] = ab2[i] * s1;
-          og[i] = abg[i] * s1;
-        }
-        wait_dw(c);  // dW2 / db2 GEMMs done: the Ubar slots may be overwritten, the dW2 regions read
-        store_chunk(Z, chunk_off(row, cg4, S::RG_Z), o0);
-        store_chunk(Z, chunk_off(row, OP / 8 + cg4, S::RG_Z), o1);
-        store_chunk(Z, chunk_off(row, 2 * OP / 8 + cg4, S::RG_Z), o2);
-        store_chunk(Z, chunk_off(row, 3 * OP / 8 + cg4, S::RG_Z), og);
-      }
-      {  // quadrant q = stream q: this lane owns row `lane` of stream q's dW2 contribution; chunks sub, (4)
-        float w[8];
-        tmem_ld8(LA + C_DW + OP * q + 8 * sub, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc2[i] += w[i];
-        if (sub == 0) {
-          tmem_ld8(LA + C_DW + OP * q + 32, w);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc2[8 + i] += w[i];
+          epi_arrive(s);
         }
       }
-      epi_arrive();
-      TC_TRACE(0, eph);
-      wait_fast(c);
-      TC_TRACE(3, eph);
-#ifdef PDEIP_TC_TRACE
-      ++eph;
-#endif
-      // ---- S11: through tanh of hidden layer 1 (while the dW1 GEMMs run), then store zbar', read dW1 ---------
-      {
-        float ab[8], ab1[8], ab2[8], abg[8], t[8];
-        tmem_ld8x4(LA + C_AB + 8 * cg4, LA + C_AB + 32 + 8 * cg4, LA + C_AB + 64 + 8 * cg4, LA + C_AB + 96 + 8 * cg4,
-                   ab, ab1, ab2, abg);
-        tmem_ld8(LA + C_T1 + 8 * cg4, t);
-        float o0[8], o1[8], og[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int un = cg4 * 8 + i;
-          const float tt = t[i], s1 = 1.f - tt * tt, s2 = -2.f * tt * s1;
-          const float z1 = ST(ST_Z10, un), zg = ST(ST_ZG0, un);  // z2_0 = 0
-          const float tb = ab[i] + ab1[i] * z1 * (-2.f * tt) + ab2[i] * (z1 * z1 * (6.f * tt * tt - 2.f)) +
-                           abg[i] * zg * (-2.f * tt);
-          o0[i] = tb * s1;
-          o1[i] = ab1[i] * s1 + ab2[i] * 2.f * s2 * z1;
-          og[i] = abg[i] * s1;
-        }
-        wait_dw(c);  // dW1 / db1 GEMMs done
-        store_chunk(Z, chunk_off(row, cg4, S::RG_Z), o0);
-        store_chunk(Z, chunk_off(row, OP / 8 + cg4, S::RG_Z), o1);
-        store_chunk(Z, chunk_off(row, 2 * OP / 8 + cg4, S::RG_Z), og);
-      }
-      {
-        float w[8];
-        tmem_ld8(LA + C_DW + 32 * q + 8 * sub, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc1[i] += w[i];
-      }
-      epi_arrive();
-      load_inputs(tile + gridDim.x);  // prefetch the next tile's x|v chunk while the dW0 GEMMs run
-      wait_dw(c);  // dW0 GEMMs done (they read the x|v|g tile, which the next tile's S0 overwrites)
-      // ---- S12: read dW0 rows (TMEM lane = unit of the x|v|g|one tile), chunk `sub` of the 32 outputs --------
-      if (q * 32 < 4 * DP) {  // warp-uniform
-        const int band = row / DP;  // 0: x rows, 1: v rows, 2: g rows, 3: the constant-one row (db0) and padding
-        const int sel = (band == 1) ? 1 : (band == 2 ? 2 : 0);
-        float w0[8], w1[8], w2[8];
-        tmem_ld8x3(LA + C_DW + 8 * sub, LA + C_DW + 32 + 8 * sub, LA + C_DW + 64 + 8 * sub, w0, w1, w2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc0[i] += (sel == 0) ? w0[i] : (sel == 1 ? w1[i] : w2[i]);
-      }
-#ifdef PDEIP_TC_TRACE
-      if (trace_on) trace[61] = clock64();
-#endif
+      first = false;
     }
+    // ---- drain: wait for P11 of the last tile of every slot (covers every MMA issued before it) --------------
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
+        ok = false;
+        atomicExch(status_w, 1);
+      }
+      par[s] ^= 1u;
+    }
+    fence_after_sync();
+    asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
 
-#ifdef PDEIP_TC_TRACE
-    if (blockIdx.x == 0 && tid == 0) (reinterpret_cast<long long*>(status) + 8)[63] = clock64();
-#endif
-    // ---- write-out: contributor slices (one writer per (slice, index)), summed in a fixed order below ----------
-    asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");  // every epilogue thread is done with the stash
-    float* red = stash;  // 4 * P + 16 * 8 floats << 80 KB
-    float* wsum = red + 4 * P;
-    for (int i = tid; i < 4 * P; i += kEpiThreads) red[i] = 0.f;
-    asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
-    {
-      float* mine = red + q * P;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mine[sh.w_off(2) + lane * kOut + sub * 8 + i] = acc2[i];
-      if (sub == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mine[sh.w_off(2) + lane * kOut + 32 + i] = acc2[8 + i];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mine[sh.w_off(1) + lane * H + sub * 8 + i] = acc1[i];
-      if (q * 32 < 4 * DP) {
-        const int band = row / DP, iu = row % DP;
-        if (band < 3 && iu < d) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) red[band * P + sh.w_off(0) + iu * H + sub * 8 + i] = acc0[i];
-        } else if (row == 3 * DP) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) red[sh.b_off(0) + sub * 8 + i] = acc0[i];
-        }
-      }
-      // db2 / db1 from the persistent regions: row of the constant-one unit (lane 3*DP), sub-warp 0 of its quadrant
-      if (q == (3 * DP) / 32 && sub == 0) {  // warp-uniform
-#pragma unroll
-        for (int cg = 0; cg < 5; ++cg) {
-          float w[8];
-          tmem_ld8(LA + C_DB2 + 8 * cg, w);
-          if (row == 3 * DP)
-            for (int i = 0; i < 8; ++i) red[sh.b_off(2) + cg * 8 + i] = w[i];
-        }
-#pragma unroll
-        for (int cg = 0; cg < 4; ++cg) {
-          float w[8];
-          tmem_ld8(LA + C_DB1 + 8 * cg, w);
-          if (row == 3 * DP)
-            for (int i = 0; i < 8; ++i) red[sh.b_off(1) + cg * 8 + i] = w[i];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < PDEIP_NUM_SUMS; ++k) {
-        const float sk = warp_sum(sums[k]);
-        if (lane == 0) wsum[warp * PDEIP_NUM_SUMS + k] = sk;
-      }
-    }
-    fence_before_sync();
-    asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+    // ---- write-out: this CTA's partial (one writer per index, fixed order -> bit-reproducible) ------------------
     float* part = a.ws + (int64_t)blockIdx.x * a.pstride;
-    if (c.ok) {
-      for (int i = tid; i < P; i += kEpiThreads) part[i] += (red[i] + red[P + i]) + (red[2 * P + i] + red[3 * P + i]);
-      if (tid < PDEIP_NUM_SUMS) {
-        float sacc = 0.f;
-        for (int w = 0; w < kEpiThreads / 32; ++w) sacc += wsum[w * PDEIP_NUM_SUMS + tid];
-        part[P + tid] += sacc;
+    float* red = reinterpret_cast<float*>(sm);  // [4 quadrants][128] bias sums + [16 warps][8] loss sums
+    const float wt = a.weight;
+    if (ok && q == 0) {  // TMEM lanes 0..31 = input unit of the dW blocks
+      const uint32_t L0 = TB;  // quadrant 0
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cg = sub + 4 * h;
+        if (cg < kOut / 8) {
+          float w[8];
+          tmem_ld8(L0 + C_DW2 + 8 * cg, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[sh.w_off(2) + lane * kOut + cg * 8 + i] += wt * w[i];
+        }
+      }
+      {
+        float w[8];
+        tmem_ld8(L0 + C_DW1 + 8 * sub, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[sh.w_off(1) + lane * H + sub * 8 + i] += wt * w[i];
+      }
+      {
+        float w[8];
+        tmem_ld8(L0 + C_DW0 + 8 * sub, w);
+        if (lane < d) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[sh.w_off(0) + lane * H + sub * 8 + i] += wt * w[i];
+        }
+      }
+    }
+    // bias gradients: sum over the 32 rows of the warp, then over the 4 quadrants through shared memory
+    // red layout: [q][0..31] db0, [32..63] db1, [64..111] db2
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r0 = warp_sum(db0a[i]), r1 = warp_sum(db1a[i]), r2 = warp_sum(db2a[i]), r3 = warp_sum(db2b[i]);
+      if (lane == 0) {
+        red[q * 128 + sub * 8 + i] = r0;
+        red[q * 128 + 32 + sub * 8 + i] = r1;
+        red[q * 128 + 64 + sub * 8 + i] = r2;
+        if (sub + 4 < OP / 8) red[q * 128 + 64 + (sub + 4) * 8 + i] = r3;
+      }
+    }
+    {
+      const float sums5[5] = {sum_g2, sum_gt2, sum_gd2, sum_d1, sum_d2};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float sk = warp_sum(sums5[k]);
+        if (lane == 0) red[512 + warp * 8 + k] = sk;
+      }
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+    if (ok) {
+      if (tid < 112) {
+        const float v = (red[tid] + red[128 + tid]) + (red[256 + tid] + red[384 + tid]);
+        if (tid < 32) part[sh.b_off(0) + tid] += wt * v;
+        else if (tid < 64) part[sh.b_off(1) + tid - 32] += wt * v;
+        else if (tid - 64 < kOut) part[sh.b_off(2) + tid - 64] += wt * v;
+      }
+      if (tid == 128) {
+        float t5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < kEpiThreads / 32; ++w)
+          for (int k = 0; k < 5; ++k) t5[k] += red[512 + w * 8 + k];
+        const float g2 = wt * t5[0], gt2 = wt * t5[1], gd2 = wt * t5[2], D1 = wt * t5[3], D2 = wt * t5[4];
+        part[P + PDEIP_SUM_G2] += g2;
+        part[P + PDEIP_SUM_GTRUE2] += gt2;
+        part[P + PDEIP_SUM_GT] += gd2;
+        part[P + PDEIP_SUM_D1] += D1;
+        part[P + PDEIP_SUM_D2] += D2;
+        part[P + PDEIP_SUM_LOSS] += g2 + gt2 - 2.f * D2 + 2.f * gamma * D1;
       }
     }
   }
+  fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(TB, 512);
 }
@@ -976,29 +829,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 static int* tensor_status_word() {
   static int* w = nullptr;
   if (!w) {
-    if (cudaMalloc(&w, 4096) != cudaSuccess) return nullptr;
-    cudaMemset(w, 0, 4096);
+    const size_t bytes = 4096 + 24 * 128 * 48 * sizeof(float);
+    if (cudaMalloc(&w, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(w, 0, bytes);
   }
   return w;
 }
 
 #ifdef PDEIP_HAVE_TENSOR_PATH
+template <int DP, int NS>
+static int launch_tc(const ResidualArgs& a, int* status, cudaStream_t st) {
+  using S = tc::Cfg<DP, NS>;
+  auto kern = tc::mlp_residual_tc_kernel<DP, NS>;
+  PDEIP_REQUIRE(true_grad_floats(a.tg, a.d) * sizeof(float) <= S::TP_BYTES, PDEIP_ERR_UNSUPPORTED,
+                "tensor path: true-gradient parameters exceed %u bytes", (unsigned)S::TP_BYTES);
+  PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+  kern<<<residual_grid(), tc::kThreads, S::TOTAL, st>>>(a, status);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
 int mlp_residual_accumulate_tensor(int set_kind, const ResidualArgs& a, int hidden, cudaStream_t st) {
   // boundary sets (two launches over n points vs n*S points of the 0T set) stay on the fp32 kernel
   if (set_kind != PDEIP_SET_KFP_0T) return mlp_residual_accumulate_fp32(set_kind, a, hidden, st);
   PDEIP_REQUIRE(hidden == 32 && a.layers == 2, PDEIP_ERR_UNSUPPORTED,
                 "tensor path is built for hidden_dim == 32, layers == 2 (got %d, %d)", hidden, a.layers);
-  PDEIP_REQUIRE(a.d >= 1 && a.d <= 16, PDEIP_ERR_UNSUPPORTED, "tensor path supports 1 <= d <= 16 (got %d)", a.d);
-  PDEIP_REQUIRE(true_grad_floats(a.tg, a.d) <= 1024, PDEIP_ERR_UNSUPPORTED,
-                "tensor path: true-gradient parameters exceed 4 KB");
+  PDEIP_REQUIRE(a.d >= 1 && a.d <= 32, PDEIP_ERR_UNSUPPORTED, "tensor path supports 1 <= d <= 32 (got %d)", a.d);
   int* status = tensor_status_word();
   PDEIP_REQUIRE(status != nullptr, PDEIP_ERR_CUDA, "cannot allocate the tensor-path status word");
-  using S = tc::Smem<16>;
-  auto kern = tc::mlp_residual_tc_kernel<16>;
-  PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-  kern<<<residual_grid(), tc::kThreads, S::TOTAL, st>>>(a, status);
-  PDEIP_LAUNCH_OK();
-  return PDEIP_OK;
+  if (a.d <= 8) return launch_tc<8, 2>(a, status, st);
+  if (a.d <= 16) return launch_tc<16, 1>(a, status, st);
+  return launch_tc<32, 1>(a, status, st);
 }
 #endif
 
@@ -1018,11 +879,14 @@ extern "C" int pdeip_tensor_path_status(void* stream, int* out_status) {
   return pdeip::tensor_path_status((cudaStream_t)stream, out_status);
 }
 
-// debug: copies the phase trace (PDEIP_TC_TRACE builds) to the host: out[64] clock stamps
-extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
+// debug (PDEIP_TC_PROBE builds): per-phase epilogue values of tile 0, [probe id][row 128][unit 48] floats
+extern "C" int pdeip_debug_tensor_probe(float* out, int n_floats) {
   int* status = pdeip::tensor_status_word();
   if (!status) return PDEIP_ERR_CUDA;
-  if (cudaMemcpy(out, reinterpret_cast<long long*>(status) + 8, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (n_floats > 24 * 128 * 48) return PDEIP_ERR_INVALID_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
+  if (cudaMemcpy(out, reinterpret_cast<float*>(status) + 64, sizeof(float) * (size_t)n_floats, cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
     return PDEIP_ERR_CUDA;
   return PDEIP_OK;
 }
