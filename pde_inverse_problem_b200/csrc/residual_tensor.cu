@@ -6,24 +6,25 @@
 //
 // Organisation.  One CTA per SM, persistent over 128-point tiles; NS tiles ("slots") are in flight per CTA so
 // that one slot's epilogue hides the other's GEMM hand-off latency (NS = 2 for d <= 8, 1 otherwise).
-//   * 16 epilogue warps: thread = (point row == TMEM lane, 8-unit chunk); 1 MMA warp: one elected lane issues
-//     every tcgen05.mma of both slots.
+//   * 8 epilogue warps: thread = (point row == TMEM lane, 16 of the 32 units / 24 of the 48 outputs); 1 MMA warp:
+//     one elected lane issues every tcgen05.mma of both slots.
 //   * operands: bf16 in shared memory, no-swizzle core-matrix layout (umma.cuh); every tile is written once and
 //     used K-major (layer GEMMs, points x units) and through the transposed view (batch-reduced dW GEMMs).
 //     Weights and the input x are split hi + lo (two bf16 terms), activations are rounded to bf16 once.
 //   * accumulators: fp32 in TMEM.  Values an epilogue needs again later are "parked" in TMEM as packed bf16 pairs
 //     (s1 = 1 - t^2 of both hidden layers, the partial seed s0p, the pz terms).
-//   * streams.  Forward Taylor streams along v: a (primal), a1, a2~ = -2 a2.  Input gradient chain za_l / aa_l.
-//     Stop-gradient stream along g~ = 2 g (order 1).  The adjoints of the a2 and g streams are proportional to the
-//     input-gradient chain (zbar2 = -2 za, zbar_g = 2 za), so only TWO adjoint streams need GEMMs: the primal
-//     (zbar0) and the order-1 stream (zbar1); the latter rides along with the input-gradient chain (P3..P5).
-//   * dW_l = t^T zbar0 + a1^T zbar1 + (a2~ + ag~)^T za accumulates over ALL tiles of the CTA in persistent TMEM
+//   * streams.  Forward Taylor streams along v: a (primal), a1, a2^ = -a2 / 2.  Input gradient chain za^ = 4 za,
+//     aa^ = 4 aa.  Stop-gradient stream along g^ = g / 2 (order 1).  The adjoints of the a2 and g streams are
+//     proportional to the input-gradient chain (zbar2 = -2 za, zbar_g = 2 za), so only TWO adjoint streams need
+//     GEMMs: the primal (zbar0) and the order-1 stream (zbar1); the latter rides along with the input-gradient chain
+//     (P3..P5).  With c = a2^ + ag^:  a2^T zbar2 + ag^T zbar_g = c^T za^.
+//   * dW_l = t^T zbar0 + a1^T zbar1 + c^T za^ accumulates over ALL tiles of the CTA in persistent TMEM
 //     columns: each term is an M = 128 GEMM over the 128 points whose A operand is the transposed view of the
 //     activation tile started at the band of that stream ("band-shifted accumulate"): rows 0..31 of D are the
 //     wanted 32 x N block, rows >= 32 are never read.  db_l = sum_p zbar0 is kept in registers.
-//   phases  P0 z0,z1_0 | P1 z1,z1_1,z2~_1 | P2 u,u1,u2~ | P3 aa2, ab1_2 (+dW2: a1) | P4 aa1, ab1_1 (+dW1: a1) |
-//           P5 g (+dW0: v) | P6 zg~_0 | P7 zg~_1 | P8 ug~ | P9 ab_2, aa2 (+dW2: t, c) | P10 ab_1, aa1 (+dW1: t, c) |
-//           P11 (dW0: x_hi, x_lo, g~).   E_k = epilogue between P_{k-1} and P_k.
+//   phases  P0 z0,z1_0 | P1 z1,z1_1,z2^_1 | P2 u,u1,u2^ | P3 aa2, ab1_2 (+dW2: a1) | P4 aa1, ab1_1 (+dW1: a1) |
+//           P5 g (+dW0: v) | P6 zg^_0 | P7 zg^_1 | P8 ug^ | P9 ab_2, aa2 (+dW2: t, c) | P10 ab_1, aa1 (+dW1: t, c) |
+//           P11 (dW0: x_hi, x_lo, g^).   E_k = epilogue between P_{k-1} and P_k.
 //   parity  rtol 1e-2 (BASELINE.json, bf16 GEMM path); measured against the oracle in tests/test_gpu_tensor.py.
 #include "mlp_thread.cuh"
 #include "residual_common.cuh"
@@ -59,15 +60,15 @@ constexpr uint32_t C_AB1 = C_R + 48, C_AA1R = C_R + 96;                     // P
 // ---- shared memory ---------------------------------------------------------------------------------------------
 // Z tile chunk map (24 chunks of 8 columns)
 constexpr int ZC_ZA2 = 0, ZC_ZA1 = 6, ZC_ZA0 = 10, ZC_TA = 14, ZC_TB = 20;
-// A tile chunk map (12 chunks): t | a1 (later the g-stream operand ag~) | a2~ (later c = a2~ + ag~)
+// A tile chunk map (12 chunks): t | a1 (later the g-stream operand ag^) | a2^ (later c = a2^ + ag^)
 constexpr int AC_T = 0, AC_A1 = 4, AC_C = 8;
 
 template <int DP, int NS>
 struct Cfg {
   static constexpr int XC = DP / 8;                  // chunks per input band
-  static constexpr int NX = 4 * XC;                  // x_hi | x_lo | v | g~
+  static constexpr int NX = 4 * XC;                  // x_hi | x_lo | v | g^
   static constexpr int KX = 2 * DP;                  // K of the x GEMM ([x_hi | x_lo] against [W0; W0])
-  static constexpr int KV = DP < 16 ? 16 : DP;       // K of the v / g~ GEMMs, N of the g GEMM
+  static constexpr int KV = DP < 16 ? 16 : DP;       // K of the v / g^ GEMMs, N of the g GEMM
   static constexpr int XC_HI = 0, XC_LO = XC, XC_V = 2 * XC, XC_G = 3 * XC;
   static constexpr uint32_t RG_X = NX * 128, RG_A = 12 * 128, RG_Z = 24 * 128;
   static constexpr uint32_t SZ_X = 16 * RG_X, SZ_A = 16 * RG_A, SZ_Z = 16 * RG_Z;
@@ -81,22 +82,37 @@ struct Cfg {
                             O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2, O_BIAS = O_T2L + SZ_T2;
   static constexpr uint32_t TP_BYTES = NS == 2 ? 2048 : 4096;
   static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
-  // prefetched input items per thread: x chunks, v chunks, (stored true gradient chunks), dealt round-robin to sub
-  static constexpr int NI = (3 * XC + 3) / 4;
 };
 
-constexpr int kEpiThreads = 512;            // 16 epilogue warps: thread = (point row, 8-unit chunk)
+constexpr int kEpiThreads = 256;            // 8 epilogue warps: thread = (point row, 16-unit half of a 32-unit tile)
 constexpr int kThreads = kEpiThreads + 32;  // + one MMA-issuing warp
 
+template <int V>
+struct IC {
+  static constexpr int value = V;
+};
+
+// PDEIP_TC_TRACE builds: clock stamps of one steady-state tile round of CTA 0: trace[(ph * 2 + slot) * 8 + k],
+// k = 0 epilogue wait start, 1 wait end, 2 arrive;  4 MMA warp operands ready, 5 fast GEMMs issued, 6 all issued
+#ifdef PDEIP_TC_TRACE
+#define TC_TRACE(k) do { if (trace_on) trace[(ph * 2 + s) * 8 + (k)] = clock64(); } while (0)
+#define TC_TRACE_DECL_MMA                                                     \
+  long long* trace = reinterpret_cast<long long*>(status) + 512;              \
+  const bool trace_on = blockIdx.x == 0 && base == (int64_t)50 * tile_stride
+#else
+#define TC_TRACE(k) do { } while (0)
+#define TC_TRACE_DECL_MMA do { } while (0)
+#endif
+
 #ifdef PDEIP_TC_PROBE
-#define TC_PROBE(id, unit0, arr)                                                              \
-  do {                                                                                        \
-    if (probe_on) {                                                                           \
-      for (int _i = 0; _i < 8; ++_i) probe[((id) * 128 + row) * 48 + (unit0) + _i] = (arr)[_i]; \
-    }                                                                                         \
+#define TC_PROBE(id, unit0, arr, n)                                                              \
+  do {                                                                                           \
+    if (probe_on) {                                                                              \
+      for (int _i = 0; _i < (n); ++_i) probe[((id) * 128 + row) * 48 + (unit0) + _i] = (arr)[_i]; \
+    }                                                                                            \
   } while (0)
 #else
-#define TC_PROBE(id, unit0, arr) do { } while (0)
+#define TC_PROBE(id, unit0, arr, n) do { } while (0)
 #endif
 
 // epilogue side: operands written -> visible to the tensor core; TMEM accesses ordered; signal the MMA warp
@@ -138,20 +154,21 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, Desc a, uint32_t a_adv, Des
 
 // NG independent forward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W^T(K-major tile [N][K]), hi + lo halves of
 // the weights, issued round-robin over g.  a_off[g] / d[g]: byte offset of the A band / TMEM column of GEMM g.
-template <int K, int N, int NG>
+template <int K, int N, int NG, bool LO = true>
 __device__ __forceinline__ void mm_fwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi, Desc w_lo) {
   constexpr uint32_t idesc = make_idesc(N, 0, 0);
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
     for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi, k * 16, idesc, k > 0 ? 1u : 0u);
+  if constexpr (!LO) return;
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
     for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
 }
 // NG backward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W (transposed view of the weight tile, rows = K)
-template <int K, int N, int NG>
+template <int K, int N, int NG, bool LO = true>
 __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi_m,
                                        Desc w_lo_m, uint32_t w_rg) {
   constexpr uint32_t idesc = make_idesc(N, 0, 1);
@@ -159,6 +176,7 @@ __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const ui
   for (int k = 0; k < K; k += 16)
 #pragma unroll
     for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi_m, (k >> 3) * w_rg, idesc, k > 0 ? 1u : 0u);
+  if constexpr (!LO) return;
 #pragma unroll
   for (int k = 0; k < K; k += 16)
 #pragma unroll
@@ -187,39 +205,136 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
-__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
-  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
-  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
-  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
-  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// 8 floats <- one 16-byte chunk of an operand tile
+__device__ __forceinline__ void load_chunk(const uint8_t* tile, uint32_t off, float* v) {
+  const uint4 q = *reinterpret_cast<const uint4*>(tile + off);
+  v[0] = bf_lo(q.x); v[1] = bf_hi(q.x); v[2] = bf_lo(q.y); v[3] = bf_hi(q.y);
+  v[4] = bf_lo(q.z); v[5] = bf_hi(q.z); v[6] = bf_lo(q.w); v[7] = bf_hi(q.w);
 }
-__device__ __forceinline__ void load_chunk(const uint8_t* tile, uint32_t off, float (&v)[8]) {
-  unpack8(*reinterpret_cast<const uint4*>(tile + off), v);
+__device__ __forceinline__ void put_chunk(uint8_t* tile, uint32_t off, const float* v) {
+  uint4 q;
+  q.x = pack2(v[0], v[1]); q.y = pack2(v[2], v[3]); q.z = pack2(v[4], v[5]); q.w = pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + off) = q;
 }
-// park 8 floats as 4 TMEM columns of packed bf16 pairs / read them back
-__device__ __forceinline__ void tmem_park8(uint32_t taddr, const float (&v)[8]) {
+// TMEM: raw loads (no wait), 8 or 16 consecutive 32-bit columns of this thread's lane
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n\t"
-      "tcgen05.wait::st.sync.aligned;\n" ::"r"(taddr),
-      "r"(pack2(v[0], v[1])), "r"(pack2(v[2], v[3])), "r"(pack2(v[4], v[5])), "r"(pack2(v[6], v[7]))
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld4_raw(uint32_t taddr, uint4& q) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\t"
-               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-               : "r"(taddr)
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, float (&v)[8]) {
-  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-               : "r"(taddr)
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
                : "memory");
-  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// NU fp32 columns (NU = 16 or 24) -> floats, no wait
+template <int NU>
+__device__ __forceinline__ void tm_ldf(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  tm_ld16(taddr, r);
+  if constexpr (NU == 24) tm_ld8(taddr + 16, r + 16);
+}
+// NU parked values = NU / 2 columns of packed bf16 pairs
+template <int NU>
+__device__ __forceinline__ void tm_ldp(uint32_t taddr, uint32_t* r) {
+  tm_ld8(taddr, r);
+  if constexpr (NU == 24) tm_ld4(taddr + 8, r + 8);
+}
+template <int NU>
+__device__ __forceinline__ void tm_park(uint32_t taddr, const float* v) {
+  uint32_t r[NU / 2];
+#pragma unroll
+  for (int i = 0; i < NU / 2; ++i) r[i] = pack2(v[2 * i], v[2 * i + 1]);
+  if constexpr (NU == 8) {
+    tm_st4(taddr, r);
+  } else {
+    tm_st8(taddr, r);
+    if constexpr (NU == 24) tm_st4(taddr + 8, r + 8);
+  }
+  tm_wait_st();
+}
+
+// inline true gradient (LINEAR: A x; GMM: core/potential.py:32-37), components [8 cg, 8 cg + 8) of point p (p < 0: none).
+// Cold path (tests and the reference-shaped API; the pipeline stores grad U next to the point): kept out of line.
+template <int DP>
+__device__ __noinline__ void true_grad_chunk(const ResidualArgs& a, const float* __restrict__ tp, int64_t p, int dimw,
+                                             int cg, float* gt) {
+  const int d = a.d;
+  float x[DP];
+#pragma unroll
+  for (int u = 0; u < DP; ++u)
+    x[u] = (p >= 0 && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
+  if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int u = cg * 8 + e;
+      float acc = 0.f;
+      if (u < d) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) acc = fmaf(tp[u * d + k], x[k], acc);
+      }
+      gt[e] = acc;
+    }
+  } else {
+    float m = -INFINITY;
+    for (int k = 0; k < a.tg.n_gaussian; ++k) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int u = 0; u < DP; ++u)
+        if (u < d) {
+          const float r = x[u] - tp[k * d + u];
+          s2 = fmaf(r, r, s2);
+        }
+      m = fmaxf(m, -0.5f * a.tg.inv_sigma2 * s2);
+    }
+    float se = 0.f, wm[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wm[e] = 0.f;
+    for (int k = 0; k < a.tg.n_gaussian; ++k) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int u = 0; u < DP; ++u)
+        if (u < d) {
+          const float r = x[u] - tp[k * d + u];
+          s2 = fmaf(r, r, s2);
+        }
+      const float ek = __expf(-0.5f * a.tg.inv_sigma2 * s2 - m);
+      se += ek;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (cg * 8 + e < d) wm[e] = fmaf(ek, tp[k * d + cg * 8 + e], wm[e]);
+    }
+    const float inv = 1.f / se;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gt[e] = (cg * 8 + e < d) ? (x[cg * 8 + e] - wm[e] * inv) * a.tg.inv_sigma2 : 0.f;
+  }
+}
+__device__ __forceinline__ float unp(const uint32_t* r, int i) { return (i & 1) ? bf_hi(r[i >> 1]) : bf_lo(r[i >> 1]); }
 
 template <int DP, int NS>
 __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
@@ -228,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma_warp = warp == kEpiThreads / 32;
   const int q = warp & 3;         // TMEM lane quadrant of this warp
-  const int sub = warp >> 2;      // which 8-unit chunk(s) this thread owns (epilogue warps: 0..3)
+  const int half = (warp >> 2) & 1;  // which 16 units of a 32-unit tile (24 of a 48-unit tile) this thread owns
   const int row = q * 32 + lane;  // point within the tile == TMEM lane == operand tile row
   const int d = a.d;
   const MlpShape<H> sh{d, 2};
@@ -312,6 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     const Desc T2HM = mk_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128), T2LM = mk_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
     constexpr uint32_t CH = 128;  // bytes per chunk (8 operand columns)
     uint32_t dw_started = 0;      // becomes 1 after the first tile's P3..P5 background GEMMs
+    // NOTE: a compact switch over the phase (about 13 KB of code) measured FASTER than the fully written-out sequence
+    // (26 KB): the epilogue warps are instruction-fetch sensitive and the larger MMA stream evicts their code.
+    // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
+    // the result is below 1e-3 (tests/tensor_v2_model.py study), the forward and input-gradient GEMMs keep hi + lo.
 #pragma unroll 1
     for (int64_t base = (int64_t)blockIdx.x * NS; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
@@ -334,11 +453,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
                 mm_fwd<S::KV, 32, 1>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);
                 commit(mb);
               } break;
-              case 1: {  // z1, z1_1, z2~_1
+              case 1: {  // z1, z1_1, z2^_1
                 mm_fwd<32, 32, 3>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
-              case 2: {  // u, u1, u2~
+              case 2: {  // u, u1, u2^
                 mm_fwd<32, OP, 3>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
@@ -357,31 +476,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
                 commit(mb);
                 mm_outer<32>(TB + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
               } break;
-              case 6: {  // zg~_0 = g~ W0
-                mm_fwd<S::KV, 32, 1>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
+              case 6: {  // zg^_0 = g^ W0
+                mm_fwd<S::KV, 32, 1, false>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
                 commit(mb);
               } break;
-              case 7: {  // zg~_1 = ag~_1 W1  (operand in the a1 band)
-                mm_fwd<32, 32, 1>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
+              case 7: {  // zg^_1 = ag^_1 W1  (operand in the a1 band)
+                mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
-              case 8: {  // ug~ = ag~_2 W2
-                mm_fwd<32, OP, 1>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
+              case 8: {  // ug^ = ag^_2 W2
+                mm_fwd<32, OP, 1, false>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
-                mm_bwd<OP, 32, 2>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                mm_bwd<OP, 32, 2, false>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
                 mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
                 mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
               } break;
               case 10: {  // ab_1 = zbar0' W1^T, aa1 again;  dW1 += t1^T zbar0' + c_1^T za1
-                mm_bwd<32, 32, 2>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                mm_bwd<32, 32, 2, false>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
                 mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
                 mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
               } break;
-              default: {  // dW0 += x_hi^T zbar0'' + x_lo^T zbar0'' + g~^T za0
+              default: {  // dW0 += x_hi^T zbar0'' + x_lo^T zbar0'' + g^^T za0
                 mm_outer<32>(TB + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
                 mm_outer<32>(TB + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
                 mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
@@ -398,348 +517,329 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     // ========================================================================================================
     // epilogue warps
     // ========================================================================================================
-    int* const status_w = status;
     bool ok = true;
     uint32_t par[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) par[s] = 0;
 #ifdef PDEIP_TC_PROBE
-    float* probe = reinterpret_cast<float*>(status) + 64;
+    float* probe = reinterpret_cast<float*>(status) + 2048;
 #endif
-    // bias-gradient sums over this thread's row (chunk `sub` of the hidden layers; chunks sub, sub + 4 of the output)
-    float db0a[8], db1a[8], db2a[8], db2b[8];
+    // bias-gradient sums over this thread's row: units [16 half, +16) of the hidden layers, [24 half, +24) of the output
+    float db0[16], db1[16], db2[24];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { db0a[i] = 0.f; db1a[i] = 0.f; db2a[i] = 0.f; db2b[i] = 0.f; }
+    for (int i = 0; i < 16; ++i) { db0[i] = 0.f; db1[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) db2[i] = 0.f;
     float sum_g2 = 0.f, sum_gt2 = 0.f, sum_gd2 = 0.f, sum_d1 = 0.f, sum_d2 = 0.f;
-    const float gamma = a.coef;
+    const float gamma = a.coef, gamma4 = 4.f * a.coef;
     const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
-    // prefetched input chunks: item j = sub + 4 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
-    float xin[NS][S::NI][8];
-    auto load_inputs = [&](int s, int64_t t) {
+    // byte offsets of this thread's row inside the operand tiles (chunk c adds c * 128)
+    const uint32_t offX = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_X;
+    const uint32_t offA = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_A;
+    const uint32_t offZ = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_Z;
+    const uint32_t LA0 = TB + ((uint32_t)(q * 32) << 16) + C_SLOT0;
+    const int u16 = 16 * half, u24 = 24 * half;  // first unit owned in 32- / 48-unit tiles
+    // prefetched input chunks: item j = half + 2 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
+    constexpr int NI = (3 * S::XC + 1) / 2;
+    float xin[NS][NI][8];
+    auto load_inputs = [&](auto Sc, int64_t t) {
+      constexpr int s = decltype(Sc)::value;
+      const int64_t pp = t * 128 + row;
+      const int64_t pc = (t < n_tiles && pp < a.n_points) ? pp : 0;
 #pragma unroll
-      for (int i = 0; i < S::NI; ++i) {
-        const int j = sub + 4 * i;
-        const int band = j / S::XC, cg = j % S::XC;
-        const int64_t pp = t * 128 + row;
-        const bool ok_p = j < 3 * S::XC && t < n_tiles && pp < a.n_points && (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS);
+      for (int i = 0; i < NI; ++i) {
+        const int j = half + 2 * i;
+        const int band = (j / S::XC) < 3 ? (j / S::XC) : 0, cg = j % S::XC;
+        const int bandc = (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS) ? band : 0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int u = cg * 8 + e;
-          xin[s][i][e] = (ok_p && u < d) ? __ldg(a.points + elem_index(a.layout, pp, band * d + u, a.n_points, dimw)) : 0.f;
+          const int uc = u < d ? u : 0;
+          xin[s][i][e] = __ldg(a.points + elem_index(a.layout, pc, bandc * d + uc, a.n_points, dimw));
         }
       }
     };
-#pragma unroll
-    for (int s = 0; s < NS; ++s) load_inputs(s, (int64_t)blockIdx.x * NS + s);
+    load_inputs(IC<0>{}, (int64_t)blockIdx.x * NS);
+    if constexpr (NS == 2) load_inputs(IC<1>{}, (int64_t)blockIdx.x * NS + 1);
 
     bool first = true;
-#pragma unroll 1
-    for (int64_t base = (int64_t)blockIdx.x * NS; base < n_tiles; base += tile_stride) {
-#pragma unroll 1
-      for (int ph = 0; ph < 12; ++ph) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          uint8_t* const X = sm + (uint32_t)s * S::SLOT + S::O_X;
-          uint8_t* const A1 = sm + (uint32_t)s * S::SLOT + S::O_A1;
-          uint8_t* const A2 = sm + (uint32_t)s * S::SLOT + S::O_A2;
-          uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z;
-          const uint32_t LA = TB + ((uint32_t)(q * 32) << 16) + C_SLOT0 + (uint32_t)s * SLOT_COLS;
-          const int64_t tile = base + s;
-          const int64_t p = tile * 128 + row;
-          const bool valid = tile < n_tiles && p < a.n_points;
-          const float mk = valid ? 1.f : 0.f;
+    int64_t base = (int64_t)blockIdx.x * NS;
+
+    // one epilogue phase of one slot: wait for the previous GEMM phase of that slot, compute, signal the MMA warp
+    auto phase = [&](auto PHc, auto Sc) {
+      constexpr int ph = decltype(PHc)::value;
+      constexpr int s = decltype(Sc)::value;
+      uint8_t* const X = sm + (uint32_t)s * S::SLOT + S::O_X + offX;
+      uint8_t* const A1 = sm + (uint32_t)s * S::SLOT + S::O_A1 + offA;
+      uint8_t* const A2 = sm + (uint32_t)s * S::SLOT + S::O_A2 + offA;
+      uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z + offZ;
+      const uint32_t LA = LA0 + (uint32_t)s * SLOT_COLS;
+      const int64_t tile = base + s;
+      const int64_t p = tile * 128 + row;
+      const bool valid = tile < n_tiles && p < a.n_points;
+      const float mk = valid ? 1.f : 0.f;
 #ifdef PDEIP_TC_PROBE
-          const bool probe_on = blockIdx.x == 0 && tile == 0;
+      const bool probe_on = blockIdx.x == 0 && tile == 0;
 #endif
-          // wait for the GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
-          if (!(first && ph == 0)) {
-            if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
-              ok = false;
-              atomicExch(status_w, 1);
-            }
-            par[s] ^= 1u;
-            fence_after_sync();
-          }
-          switch (ph) {
-            case 0: {  // E0: x (hi + lo) and v bands of this tile; prefetch registers are refilled in E1
-#pragma unroll
-              for (int i = 0; i < S::NI; ++i) {
-                const int j = sub + 4 * i;
-                const int band = j / S::XC, cg = j % S::XC;
-                if (band == 0) {
-                  float hi[8], lo[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    hi[e] = __bfloat162float(__float2bfloat16_rn(xin[s][i][e]));
-                    lo[e] = xin[s][i][e] - hi[e];
-                  }
-                  store_chunk(X, chunk_off(row, S::XC_HI + cg, S::RG_X), hi);
-                  store_chunk(X, chunk_off(row, S::XC_LO + cg, S::RG_X), lo);
-                } else if (band == 1) {
-                  store_chunk(X, chunk_off(row, S::XC_V + cg, S::RG_X), xin[s][i]);
-                }
-              }
-            } break;
-            case 1: {  // E1: t1, a1_1, a2~_1 = 4 t a1 z1
-              float z0[8], z1[8], t[8], s1[8], q1[8], q2[8];
-              tmem_ld8x2(LA + C_Z0 + 8 * sub, LA + C_Z10 + 8 * sub, z0, z1);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                t[i] = tanh_fast(z0[i] + bias_s[sub * 8 + i]);
-                s1[i] = 1.f - t[i] * t[i];
-                q1[i] = s1[i] * z1[i];
-                q2[i] = 4.f * t[i] * q1[i] * z1[i];
-              }
-              store_chunk(A1, chunk_off(row, AC_T + sub, S::RG_A), t);
-              store_chunk(A1, chunk_off(row, AC_A1 + sub, S::RG_A), q1);
-              store_chunk(A1, chunk_off(row, AC_C + sub, S::RG_A), q2);
-              tmem_park8(LA + C_S1P1 + 4 * sub, s1);
-              TC_PROBE(0, sub * 8, t);
-              TC_PROBE(1, sub * 8, q1);
-              TC_PROBE(2, sub * 8, q2);
-            } break;
-            case 2: {  // E2: t2, a1_2, a2~_2 = s1 z2~ + 4 t a1 z1
-              float z0[8], z1[8], z2[8], t[8], s1[8], q1[8], q2[8];
-              tmem_ld8x3(LA + C_Z1 + 8 * sub, LA + C_Z11 + 8 * sub, LA + C_Z21 + 8 * sub, z0, z1, z2);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                t[i] = tanh_fast(z0[i] + bias_s[32 + sub * 8 + i]);
-                s1[i] = 1.f - t[i] * t[i];
-                q1[i] = s1[i] * z1[i];
-                q2[i] = fmaf(s1[i], z2[i], 4.f * t[i] * q1[i] * z1[i]);
-              }
-              store_chunk(A2, chunk_off(row, AC_T + sub, S::RG_A), t);
-              store_chunk(A2, chunk_off(row, AC_A1 + sub, S::RG_A), q1);
-              store_chunk(A2, chunk_off(row, AC_C + sub, S::RG_A), q2);
-              tmem_park8(LA + C_S1P2 + 4 * sub, s1);
-              TC_PROBE(3, sub * 8, t);
-              TC_PROBE(4, sub * 8, q1);
-              TC_PROBE(5, sub * 8, q2);
-            } break;
-            case 3: {  // E3: za2 = 2u, s1v, s0p, D_v V, D_v^2 V
-              float d1 = 0.f, d2a = 0.f, d2b = 0.f;
-#pragma unroll 1
-              for (int cg = sub; cg < OP / 8; cg += 4) {
-                float u[8], u1[8], u2[8], za[8], sv[8], sp[8];
-                tmem_ld8x3(LA + C_U + 8 * cg, LA + C_U1 + 8 * cg, LA + C_U2 + 8 * cg, u, u1, u2);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float uu = u[i] + bias_s[64 + cg * 8 + i];
-                  d1 = fmaf(uu, u1[i], d1);
-                  d2a = fmaf(u1[i], u1[i], d2a);
-                  d2b = fmaf(uu, u2[i], d2b);
-                  za[i] = 2.f * mk * uu;
-                  sv[i] = mk * fmaf(-8.f, u1[i], 4.f * gamma * uu);
-                  sp[i] = mk * fmaf(2.f, u2[i], 4.f * gamma * u1[i]);
-                }
-                store_chunk(Z, chunk_off(row, ZC_ZA2 + cg, S::RG_Z), za);
-                store_chunk(Z, chunk_off(row, ZC_TA + cg, S::RG_Z), sv);
-                tmem_park8(LA + C_S0P + 4 * cg, sp);
-                TC_PROBE(6, cg * 8, za);
-                TC_PROBE(7, cg * 8, sv);
-                TC_PROBE(8, cg * 8, sp);
-              }
-              // this thread's share of D_v V = 2 u.u1 and D_v^2 V = 2 (u1.u1 + u.u2), u2 = -u2~ / 2
-              sum_d1 += mk * 2.f * d1;
-              sum_d2 += mk * (2.f * d2a - d2b);
-            } break;
-            case 4:    // E4: za1, zbar1', pz2  (hidden layer 2)
-            case 5: {  // E5: za0, zbar1'', pz1 (hidden layer 1)
-              const bool l2 = ph == 4;
-              const uint8_t* At = l2 ? A2 : A1;
-              float aa[8], ab1[8], s1[8], t[8], a1[8], za[8], zb[8], pz[8];
-              uint4 s1q;
-              tmem_ld8_raw(LA + (l2 ? C_AA2 : C_AA1) + 8 * sub, aa);
-              tmem_ld8_raw(LA + (l2 ? C_AB12 : C_AB11) + 8 * sub, ab1);
-              tmem_ld4_raw(LA + (l2 ? C_S1P2 : C_S1P1) + 4 * sub, s1q);
-              load_chunk(At, chunk_off(row, AC_T + sub, S::RG_A), t);
-              load_chunk(At, chunk_off(row, AC_A1 + sub, S::RG_A), a1);
-              tmem_wait_ld();
-              unpack8(s1q, s1);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                za[i] = aa[i] * s1[i];
-                const float qq = aa[i] * a1[i];
-                zb[i] = fmaf(s1[i], ab1[i], 8.f * t[i] * qq);
-                pz[i] = fmaf(-2.f * t[i] * ab1[i], a1[i], 4.f * qq * a1[i]);
-              }
-              store_chunk(Z, chunk_off(row, (l2 ? ZC_ZA1 : ZC_ZA0) + sub, S::RG_Z), za);
-              store_chunk(Z, chunk_off(row, (l2 ? ZC_TB : ZC_TA) + sub, S::RG_Z), zb);
-              tmem_park8(LA + (l2 ? C_PZ2 : C_PZ1) + 4 * sub, pz);
-              TC_PROBE(l2 ? 9 : 12, sub * 8, za);
-              TC_PROBE(l2 ? 10 : 13, sub * 8, zb);
-              TC_PROBE(l2 ? 11 : 14, sub * 8, pz);
-            } break;
-            case 6: {  // E6: g~ = 2 g band; |g|^2, |g_true|^2, |g_true - g|^2
-              // item j of this thread: band 2 (stored true gradient) chunks own the sums when the gradient is stored;
-              // otherwise the x-chunk owners do (they hold x for the inline true gradient)
-#pragma unroll
-              for (int i = 0; i < S::NI; ++i) {
-                const int j = sub + 4 * i;
-                const int band = j / S::XC, cg = j % S::XC;
-                if (j < 3 * S::XC && band == 0) {  // writes the g~ chunk
-                  float gv[8], g2v[8];
-                  tmem_ld8(LA + C_G + 8 * cg, gv);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) g2v[e] = 2.f * gv[e];
-                  store_chunk(X, chunk_off(row, S::XC_G + cg, S::RG_X), g2v);
-                  TC_PROBE(15, cg * 8, gv);
-                  if (a.tg.kind != PDEIP_DRIFT_IN_POINTS) {
-                    float gt[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) gt[e] = 0.f;
-                    if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
-                      float x[DP];
-#pragma unroll
-                      for (int u = 0; u < DP; ++u)
-                        x[u] = (valid && u < d) ? __ldg(a.points + elem_index(a.layout, p, u, a.n_points, dimw)) : 0.f;
-                      if (a.tg.kind == PDEIP_DRIFT_LINEAR) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                          const int u = cg * 8 + e;
-                          if (u < d) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int k = 0; k < DP; ++k)
-                              if (k < d) acc = fmaf(tp[u * d + k], x[k], acc);
-                            gt[e] = acc;
-                          }
-                        }
-                      } else {
-                        float m = -INFINITY;
-                        for (int k = 0; k < a.tg.n_gaussian; ++k) {
-                          float s2 = 0.f;
-#pragma unroll
-                          for (int u = 0; u < DP; ++u)
-                            if (u < d) {
-                              const float r = x[u] - tp[k * d + u];
-                              s2 = fmaf(r, r, s2);
-                            }
-                          m = fmaxf(m, -0.5f * a.tg.inv_sigma2 * s2);
-                        }
-                        float se = 0.f, wm[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) wm[e] = 0.f;
-                        for (int k = 0; k < a.tg.n_gaussian; ++k) {
-                          float s2 = 0.f;
-#pragma unroll
-                          for (int u = 0; u < DP; ++u)
-                            if (u < d) {
-                              const float r = x[u] - tp[k * d + u];
-                              s2 = fmaf(r, r, s2);
-                            }
-                          const float ek = __expf(-0.5f * a.tg.inv_sigma2 * s2 - m);
-                          se += ek;
-#pragma unroll
-                          for (int e = 0; e < 8; ++e)
-                            if (cg * 8 + e < d) wm[e] = fmaf(ek, tp[k * d + cg * 8 + e], wm[e]);
-                        }
-                        const float inv = 1.f / se;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                          if (cg * 8 + e < d) gt[e] = (x[cg * 8 + e] - wm[e] * inv) * a.tg.inv_sigma2;
-                      }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
-                      sum_gt2 = fmaf(mk * gt[e], gt[e], sum_gt2);
-                      sum_gd2 = fmaf(mk * (gt[e] - gv[e]), gt[e] - gv[e], sum_gd2);
-                    }
-                  }
-                } else if (j < 3 * S::XC && band == 2 && a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
-                  float gv[8];
-                  tmem_ld8(LA + C_G + 8 * cg, gv);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float gt = xin[s][i][e];
-                    sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
-                    sum_gt2 = fmaf(mk * gt, gt, sum_gt2);
-                    sum_gd2 = fmaf(mk * (gt - gv[e]), gt - gv[e], sum_gd2);
-                  }
-                }
-              }
-            } break;
-            case 7:    // E7: ag~_1 = s1_1 zg~_0 -> a1 band of A1;  c_1 = a2~_1 + ag~_1
-            case 8: {  // E8: ag~_2 = s1_2 zg~_1 -> a1 band of A2;  c_2
-              const bool l1 = ph == 7;
-              uint8_t* At = l1 ? A1 : A2;
-              float zg[8], s1[8], a2[8], ag[8], c[8];
-              uint4 s1q;
-              tmem_ld8_raw(LA + (l1 ? C_ZG0 : C_ZG1) + 8 * sub, zg);
-              tmem_ld4_raw(LA + (l1 ? C_S1P1 : C_S1P2) + 4 * sub, s1q);
-              load_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), a2);
-              tmem_wait_ld();
-              unpack8(s1q, s1);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                ag[i] = s1[i] * zg[i];
-                c[i] = a2[i] + ag[i];
-              }
-              store_chunk(At, chunk_off(row, AC_A1 + sub, S::RG_A), ag);
-              store_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), c);
-              TC_PROBE(l1 ? 16 : 17, sub * 8, c);
-            } break;
-            case 9: {  // E9: s0 = s0p + 2 ug~;  db2 += s0
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int cg = sub + 4 * h;
-                if (cg < OP / 8) {
-                  float ug[8], sp[8], s0[8];
-                  uint4 spq;
-                  tmem_ld8_raw(LA + C_UG + 8 * cg, ug);
-                  tmem_ld4_raw(LA + C_S0P + 4 * cg, spq);
-                  tmem_wait_ld();
-                  unpack8(spq, sp);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    s0[i] = fmaf(2.f, ug[i], sp[i]);
-                    if (h == 0) db2a[i] += s0[i];
-                    else db2b[i] += s0[i];
-                  }
-                  store_chunk(Z, chunk_off(row, ZC_TA + cg, S::RG_Z), s0);
-                  TC_PROBE(18, cg * 8, s0);
-                }
-              }
-            } break;
-            case 10:    // E10: zbar0' = s1_2 ab_2 + pz2 - 2 t2 aa2 c_2;  db1
-            default: {  // E11: zbar0'' = s1_1 ab_1 + pz1 - 2 t1 aa1 c_1;  db0
-              const bool l2 = ph == 10;
-              const uint8_t* At = l2 ? A2 : A1;
-              float ab[8], aa[8], s1[8], pz[8], t[8], c[8], zb[8];
-              uint4 s1q, pzq;
-              tmem_ld8_raw(LA + (l2 ? C_AB2 : C_AB1) + 8 * sub, ab);
-              tmem_ld8_raw(LA + (l2 ? C_AA2R : C_AA1R) + 8 * sub, aa);
-              tmem_ld4_raw(LA + (l2 ? C_S1P2 : C_S1P1) + 4 * sub, s1q);
-              tmem_ld4_raw(LA + (l2 ? C_PZ2 : C_PZ1) + 4 * sub, pzq);
-              load_chunk(At, chunk_off(row, AC_T + sub, S::RG_A), t);
-              load_chunk(At, chunk_off(row, AC_C + sub, S::RG_A), c);
-              tmem_wait_ld();
-              unpack8(s1q, s1);
-              unpack8(pzq, pz);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                zb[i] = fmaf(s1[i], ab[i], fmaf(-2.f * t[i] * aa[i], c[i], pz[i]));
-                if (l2) db1a[i] += zb[i];
-                else db0a[i] += zb[i];
-              }
-              store_chunk(Z, chunk_off(row, (l2 ? ZC_TB : ZC_TA) + sub, S::RG_Z), zb);
-              TC_PROBE(l2 ? 19 : 20, sub * 8, zb);
-              // prefetch the next tile of this slot while its last GEMMs run
-              if (!l2) load_inputs(s, tile + tile_stride);
-            } break;
-          }
-          epi_arrive(s);
+      if (!(ph == 0 && first)) {  // GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
+        if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
+          ok = false;
+          atomicExch(status, 1);
         }
+        par[s] ^= 1u;
+        fence_after_sync();
       }
+      if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int j = half + 2 * i;
+          const int band = j / S::XC, cg = j % S::XC;
+          if (band == 0) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float xv = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
+              hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
+              lo[e] = xv - hi[e];
+            }
+            put_chunk(X, (S::XC_HI + cg) * 128, hi);
+            put_chunk(X, (S::XC_LO + cg) * 128, lo);
+          } else if (band == 1) {
+            float vv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vv[e] = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
+            put_chunk(X, (S::XC_V + cg) * 128, vv);
+          }
+        }
+      } else if constexpr (ph == 1 || ph == 2) {
+        // E1: t1, a1_1 = s1 z1, a2^_1 = t a1 z1      E2: t2, a1_2, a2^_2 = s1 z2^ + t a1 z1     (a2^ = -a2 / 2)
+        constexpr bool l1 = ph == 1;
+        uint8_t* const At = l1 ? A1 : A2;
+        float z0[16], z1[16], z2[16];
+        tm_ldf<16>(LA + (l1 ? C_Z0 : C_Z1) + u16, z0);
+        tm_ldf<16>(LA + (l1 ? C_Z10 : C_Z11) + u16, z1);
+        if constexpr (!l1) tm_ldf<16>(LA + C_Z21 + u16, z2);
+        float bb[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(bias_s + (l1 ? 0 : 32) + u16 + 4 * i);
+        tm_wait_ld();
+        float t[16], s1[16], q1[16], q2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          t[i] = tanh_fast(z0[i] + bb[i]);
+          s1[i] = fmaf(-t[i], t[i], 1.f);
+          q1[i] = s1[i] * z1[i];
+          const float w = t[i] * q1[i];
+          q2[i] = l1 ? w * z1[i] : fmaf(s1[i], z2[i], w * z1[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          put_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
+          put_chunk(At, (AC_A1 + 2 * half + c) * 128, q1 + 8 * c);
+          put_chunk(At, (AC_C + 2 * half + c) * 128, q2 + 8 * c);
+        }
+        tm_park<16>(LA + (l1 ? C_S1P1 : C_S1P2) + 8 * half, s1);
+        TC_PROBE(l1 ? 0 : 3, u16, t, 16);
+        TC_PROBE(l1 ? 1 : 4, u16, q1, 16);
+        TC_PROBE(l1 ? 2 : 5, u16, q2, 16);
+      } else if constexpr (ph == 3) {
+        // E3: za^2 = 8 u, s1v = -8 u1 + 4 gamma u, s0p = 8 u2^ + 4 gamma u1, D_v V, D_v^2 V
+        float u[24], u1[24], u2[24];
+        tm_ldf<24>(LA + C_U + u24, u);
+        tm_ldf<24>(LA + C_U1 + u24, u1);
+        tm_ldf<24>(LA + C_U2 + u24, u2);
+        float bb[24];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(bias_s + 64 + u24 + 4 * i);
+        tm_wait_ld();
+        const float k8 = 8.f * mk, kg = gamma4 * mk;
+        float d1 = 0.f, d2a = 0.f, d2b = 0.f;
+        float za[24], sv[24], sp[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+          const float uu = u[i] + bb[i];
+          d1 = fmaf(uu, u1[i], d1);
+          d2a = fmaf(u1[i], u1[i], d2a);
+          d2b = fmaf(uu, u2[i], d2b);
+          za[i] = k8 * uu;
+          sv[i] = fmaf(-k8, u1[i], kg * uu);
+          sp[i] = fmaf(k8, u2[i], kg * u1[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          put_chunk(Z, (ZC_ZA2 + 3 * half + c) * 128, za + 8 * c);
+          put_chunk(Z, (ZC_TA + 3 * half + c) * 128, sv + 8 * c);
+        }
+        tm_park<24>(LA + C_S0P + 12 * half, sp);
+        // this thread's share of D_v V = 2 u.u1 and D_v^2 V = 2 (u1.u1 + u.u2), u2 = -2 u2^
+        sum_d1 = fmaf(2.f * mk, d1, sum_d1);
+        sum_d2 = fmaf(mk, 2.f * d2a - 4.f * d2b, sum_d2);
+        TC_PROBE(6, u24, za, 24);
+        TC_PROBE(7, u24, sv, 24);
+        TC_PROBE(8, u24, sp, 24);
+      } else if constexpr (ph == 4 || ph == 5) {
+        // E4 (hidden layer 2) / E5 (hidden layer 1):  aa^ = 4 aa from the GEMM of za^
+        //   za^' = aa^ s1,  zbar1' = s1 ab1 + 2 t aa^ a1,  pz = a1 (aa^ a1 - 2 t ab1)
+        constexpr bool l2 = ph == 4;
+        const uint8_t* At = l2 ? A2 : A1;
+        float aa[16], ab1[16], t[16], a1[16];
+        uint32_t s1p[8];
+        tm_ldf<16>(LA + (l2 ? C_AA2 : C_AA1) + u16, aa);
+        tm_ldf<16>(LA + (l2 ? C_AB12 : C_AB11) + u16, ab1);
+        tm_ldp<16>(LA + (l2 ? C_S1P2 : C_S1P1) + 8 * half, s1p);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          load_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
+          load_chunk(At, (AC_A1 + 2 * half + c) * 128, a1 + 8 * c);
+        }
+        tm_wait_ld();
+        float za[16], zb[16], pz[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float s1 = unp(s1p, i);
+          za[i] = aa[i] * s1;
+          const float qq = aa[i] * a1[i];
+          zb[i] = fmaf(2.f * t[i], qq, s1 * ab1[i]);
+          pz[i] = a1[i] * fmaf(-2.f * t[i], ab1[i], qq);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          put_chunk(Z, ((l2 ? ZC_ZA1 : ZC_ZA0) + 2 * half + c) * 128, za + 8 * c);
+          put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
+        }
+        tm_park<16>(LA + (l2 ? C_PZ2 : C_PZ1) + 8 * half, pz);
+        TC_PROBE(l2 ? 9 : 12, u16, za, 16);
+        TC_PROBE(l2 ? 10 : 13, u16, zb, 16);
+        TC_PROBE(l2 ? 11 : 14, u16, pz, 16);
+      } else if constexpr (ph == 6) {
+        // E6: g^ = g / 2 band (the GEMM gives 4 g);  |g|^2, |g_true|^2, |g_true - g|^2
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int j = half + 2 * i;
+          const int band = j / S::XC, cg = j % S::XC;
+          const bool own_sum = a.tg.kind == PDEIP_DRIFT_IN_POINTS ? band == 2 : band == 0;
+          if (j < 3 * S::XC && (band == 0 || own_sum)) {
+            float g4[8], gv[8], gt[8];
+            tm_ld8(LA + C_G + 8 * cg, reinterpret_cast<uint32_t*>(g4));
+            tm_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              gv[e] = 0.25f * g4[e];
+              gt[e] = 0.f;
+            }
+            if (band == 0) {
+              float gh[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gh[e] = 0.125f * g4[e];
+              put_chunk(X, (S::XC_G + cg) * 128, gh);
+              TC_PROBE(15, cg * 8, gv, 8);
+            }
+            if (own_sum) {
+              if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gt[e] = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
+              } else if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
+                true_grad_chunk<DP>(a, tp, valid ? p : (int64_t)-1, dimw, cg, gt);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float df = gt[e] - gv[e];
+                sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
+                sum_gt2 = fmaf(mk * gt[e], gt[e], sum_gt2);
+                sum_gd2 = fmaf(mk * df, df, sum_gd2);
+              }
+            }
+          }
+        }
+      } else if constexpr (ph == 7 || ph == 8) {
+        // E7: ag^_1 = s1_1 zg^_0 -> a1 band of A1;  c_1 = a2^_1 + ag^_1       E8: the same for hidden layer 2
+        constexpr bool l1 = ph == 7;
+        uint8_t* const At = l1 ? A1 : A2;
+        float zg[16], a2[16];
+        uint32_t s1p[8];
+        tm_ldf<16>(LA + (l1 ? C_ZG0 : C_ZG1) + u16, zg);
+        tm_ldp<16>(LA + (l1 ? C_S1P1 : C_S1P2) + 8 * half, s1p);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) load_chunk(At, (AC_C + 2 * half + c) * 128, a2 + 8 * c);
+        tm_wait_ld();
+        float ag[16], cc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          ag[i] = unp(s1p, i) * zg[i];
+          cc[i] = a2[i] + ag[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          put_chunk(At, (AC_A1 + 2 * half + c) * 128, ag + 8 * c);
+          put_chunk(At, (AC_C + 2 * half + c) * 128, cc + 8 * c);
+        }
+        TC_PROBE(l1 ? 16 : 17, u16, cc, 16);
+      } else if constexpr (ph == 9) {
+        // E9: s0 = s0p + 8 ug^;  db2 += s0
+        float ug[24], s0[24];
+        uint32_t spp[12];
+        tm_ldf<24>(LA + C_UG + u24, ug);
+        tm_ldp<24>(LA + C_S0P + 12 * half, spp);
+        tm_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+          s0[i] = fmaf(8.f, ug[i], unp(spp, i));
+          db2[i] += s0[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put_chunk(Z, (ZC_TA + 3 * half + c) * 128, s0 + 8 * c);
+        TC_PROBE(18, u24, s0, 24);
+      } else {
+        // E10: zbar0' = s1_2 ab_2 + pz2 - 2 t2 aa^2 c_2;  db1       E11: zbar0'' likewise with hidden layer 1;  db0
+        constexpr bool l2 = ph == 10;
+        const uint8_t* At = l2 ? A2 : A1;
+        float ab[16], aa[16], t[16], cc[16];
+        uint32_t s1p[8], pzp[8];
+        tm_ldf<16>(LA + (l2 ? C_AB2 : C_AB1) + u16, ab);
+        tm_ldf<16>(LA + (l2 ? C_AA2R : C_AA1R) + u16, aa);
+        tm_ldp<16>(LA + (l2 ? C_S1P2 : C_S1P1) + 8 * half, s1p);
+        tm_ldp<16>(LA + (l2 ? C_PZ2 : C_PZ1) + 8 * half, pzp);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          load_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
+          load_chunk(At, (AC_C + 2 * half + c) * 128, cc + 8 * c);
+        }
+        tm_wait_ld();
+        float zb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float m0 = fmaf(unp(s1p, i), ab[i], unp(pzp, i));
+          zb[i] = fmaf(-2.f * t[i] * aa[i], cc[i], m0);
+          if (l2) db1[i] += zb[i];
+          else db0[i] += zb[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
+        TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
+        // prefetch the next tile of this slot while its last GEMMs run
+        if constexpr (!l2) load_inputs(Sc, tile + tile_stride);
+      }
+      epi_arrive(s);
+    };
+#define PDEIP_TC_PHASE(PH)                       \
+  phase(IC<PH>{}, IC<0>{});                      \
+  if constexpr (NS == 2) phase(IC<PH>{}, IC<1>{});
+
+#pragma unroll 1
+    for (; base < n_tiles; base += tile_stride) {
+      PDEIP_TC_PHASE(0) PDEIP_TC_PHASE(1) PDEIP_TC_PHASE(2) PDEIP_TC_PHASE(3) PDEIP_TC_PHASE(4) PDEIP_TC_PHASE(5)
+      PDEIP_TC_PHASE(6) PDEIP_TC_PHASE(7) PDEIP_TC_PHASE(8) PDEIP_TC_PHASE(9) PDEIP_TC_PHASE(10) PDEIP_TC_PHASE(11)
       first = false;
     }
+#undef PDEIP_TC_PHASE
     // ---- drain: wait for P11 of the last tile of every slot (covers every MMA issued before it) --------------
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
         ok = false;
-        atomicExch(status_w, 1);
+        atomicExch(status, 1);
       }
       par[s] ^= 1u;
     }
@@ -748,46 +848,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 
     // ---- write-out: this CTA's partial (one writer per index, fixed order -> bit-reproducible) ------------------
     float* part = a.ws + (int64_t)blockIdx.x * a.pstride;
-    float* red = reinterpret_cast<float*>(sm);  // [4 quadrants][128] bias sums + [16 warps][8] loss sums
+    float* red = reinterpret_cast<float*>(sm);  // [4 quadrants][128] bias sums + [8 warps][8] loss sums
     const float wt = a.weight;
     if (ok && q == 0) {  // TMEM lanes 0..31 = input unit of the dW blocks
-      const uint32_t L0 = TB;  // quadrant 0
+      float w2[24], w1[16], w0[16];
+      tm_ldf<24>(TB + C_DW2 + u24, w2);
+      tm_ldf<16>(TB + C_DW1 + u16, w1);
+      tm_ldf<16>(TB + C_DW0 + u16, w0);
+      tm_wait_ld();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int cg = sub + 4 * h;
-        if (cg < kOut / 8) {
-          float w[8];
-          tmem_ld8(L0 + C_DW2 + 8 * cg, w);
+      for (int i = 0; i < 24; ++i)
+        if (u24 + i < kOut) part[sh.w_off(2) + lane * kOut + u24 + i] += wt * w2[i];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) part[sh.w_off(2) + lane * kOut + cg * 8 + i] += wt * w[i];
-        }
-      }
-      {
-        float w[8];
-        tmem_ld8(L0 + C_DW1 + 8 * sub, w);
+      for (int i = 0; i < 16; ++i) part[sh.w_off(1) + lane * H + u16 + i] += wt * w1[i];
+      if (lane < d) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) part[sh.w_off(1) + lane * H + sub * 8 + i] += wt * w[i];
-      }
-      {
-        float w[8];
-        tmem_ld8(L0 + C_DW0 + 8 * sub, w);
-        if (lane < d) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) part[sh.w_off(0) + lane * H + sub * 8 + i] += wt * w[i];
-        }
+        for (int i = 0; i < 16; ++i) part[sh.w_off(0) + lane * H + u16 + i] += wt * w0[i];
       }
     }
     // bias gradients: sum over the 32 rows of the warp, then over the 4 quadrants through shared memory
     // red layout: [q][0..31] db0, [32..63] db1, [64..111] db2
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float r0 = warp_sum(db0a[i]), r1 = warp_sum(db1a[i]), r2 = warp_sum(db2a[i]), r3 = warp_sum(db2b[i]);
+    for (int i = 0; i < 16; ++i) {
+      const float r0 = warp_sum(db0[i]), r1 = warp_sum(db1[i]);
       if (lane == 0) {
-        red[q * 128 + sub * 8 + i] = r0;
-        red[q * 128 + 32 + sub * 8 + i] = r1;
-        red[q * 128 + 64 + sub * 8 + i] = r2;
-        if (sub + 4 < OP / 8) red[q * 128 + 64 + (sub + 4) * 8 + i] = r3;
+        red[q * 128 + u16 + i] = r0;
+        red[q * 128 + 32 + u16 + i] = r1;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      const float r2 = warp_sum(db2[i]);
+      if (lane == 0) red[q * 128 + 64 + u24 + i] = r2;
     }
     {
       const float sums5[5] = {sum_g2, sum_gt2, sum_gd2, sum_d1, sum_d2};
@@ -829,7 +921,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 static int* tensor_status_word() {
   static int* w = nullptr;
   if (!w) {
-    const size_t bytes = 4096 + 24 * 128 * 48 * sizeof(float);
+    const size_t bytes = 8192 + 24 * 128 * 48 * sizeof(float);
     if (cudaMalloc(&w, bytes) != cudaSuccess) return nullptr;
     cudaMemset(w, 0, bytes);
   }
@@ -879,13 +971,25 @@ extern "C" int pdeip_tensor_path_status(void* stream, int* out_status) {
   return pdeip::tensor_path_status((cudaStream_t)stream, out_status);
 }
 
+// debug (PDEIP_TC_TRACE builds): 24 x 8 clock stamps (see TC_TRACE)
+extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
+  int* status = pdeip::tensor_status_word();
+  if (!status) return PDEIP_ERR_CUDA;
+  if (n > 24 * 8) return PDEIP_ERR_INVALID_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
+  if (cudaMemcpy(out, reinterpret_cast<long long*>(status) + 512, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
+    return PDEIP_ERR_CUDA;
+  return PDEIP_OK;
+}
+
 // debug (PDEIP_TC_PROBE builds): per-phase epilogue values of tile 0, [probe id][row 128][unit 48] floats
 extern "C" int pdeip_debug_tensor_probe(float* out, int n_floats) {
   int* status = pdeip::tensor_status_word();
   if (!status) return PDEIP_ERR_CUDA;
   if (n_floats > 24 * 128 * 48) return PDEIP_ERR_INVALID_ARG;
   if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
-  if (cudaMemcpy(out, reinterpret_cast<float*>(status) + 64, sizeof(float) * (size_t)n_floats, cudaMemcpyDeviceToHost) !=
+  if (cudaMemcpy(out, reinterpret_cast<float*>(status) + 2048, sizeof(float) * (size_t)n_floats, cudaMemcpyDeviceToHost) !=
       cudaSuccess)
     return PDEIP_ERR_CUDA;
   return PDEIP_OK;

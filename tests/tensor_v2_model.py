@@ -1,8 +1,8 @@
 """Plain-torch statement of the phase schedule of the tcgen05 residual kernel (csrc/residual_tensor.cu, v2).
 
 TEST INFRASTRUCTURE: it restates, phase by phase (P = GEMM phase, E = epilogue), exactly what the kernel computes,
-in float64 and without any bf16 rounding, so that (a) the algebra of the schedule (tilded streams a2~ = -2 a2,
-g~ = 2 g; adjoints of the order-2 and g streams taken from the input-gradient chain; pz terms; merged band
+in float64 and without any bf16 rounding, so that (a) the algebra of the schedule (rescaled streams a2^ = -a2/2,
+g^ = g/2, input-gradient chain za^ = 4 za; adjoints of the order-2 and g streams taken from the input-gradient chain; pz terms; merged band
 c = a2~ + ag~) is checked against oracle/taylor.py on the CPU, and (b) the per-phase probe dumps of the kernel can be
 compared with `trace` on the GPU.  KFP 0T set (kinetic_fokker_planck.py:40-45): per point
 |g|^2 - 2 D_v^2 V + 2 gamma D_v V, 3-Dense-layer MLP d -> H -> H -> O.
@@ -32,7 +32,7 @@ def kfp_0T_schedule(W, b, x, v, gamma: float, weight: float, mask=None, emulate_
     t1 = torch.tanh(z0 + b0)
     s11 = 1 - t1 * t1
     a11 = s11 * z10
-    a2t1 = 4 * t1 * a11 * z10
+    a2t1 = t1 * a11 * z10                    # a2^ = -a2 / 2
     t1, s11, a11, a2t1 = r(t1), r(s11), r(a11), r(a2t1)   # operand bands / parked s1 (epilogues later read these)
     tr.update(t1=t1, s1_1=s11, a1_1=a11, a2t_1=a2t1)
     # P1 / E2
@@ -40,38 +40,38 @@ def kfp_0T_schedule(W, b, x, v, gamma: float, weight: float, mask=None, emulate_
     t2 = torch.tanh(z1 + b1)
     s12 = 1 - t2 * t2
     a12 = s12 * z11
-    a2t2 = s12 * z21t + 4 * t2 * a12 * z11
+    a2t2 = s12 * z21t + t2 * a12 * z11
     t2, s12, a12, a2t2 = r(t2), r(s12), r(a12), r(a2t2)
     tr.update(t2=t2, s1_2=s12, a1_2=a12, a2t_2=a2t2)
     # P2 / E3
     u, u1, u2t = t2 @ W2, a12 @ W2, a2t2 @ W2
     uu = u + b2
-    za2 = r(2 * uu * m)
+    za2 = r(8 * uu * m)                      # za^ = 4 za
     D1 = 2 * (uu * u1).sum(-1, keepdim=True)
-    D2 = 2 * ((u1 * u1).sum(-1, keepdim=True) - 0.5 * (uu * u2t).sum(-1, keepdim=True))
+    D2 = 2 * ((u1 * u1).sum(-1, keepdim=True) - 2 * (uu * u2t).sum(-1, keepdim=True))
     s1v = r((-8 * u1 + 4 * gamma * uu) * m)
-    s0p = r((2 * u2t + 4 * gamma * u1) * m)
+    s0p = r((8 * u2t + 4 * gamma * u1) * m)
     tr.update(za2=za2, s1v=s1v, s0p=s0p)
     # P3 / E4
     aa2, ab12 = za2 @ W2.T, s1v @ W2.T
     dW2 = a12.T @ s1v
     za1 = r(aa2 * s12)
     q = aa2 * a12
-    zb1p = r(s12 * ab12 + 8 * t2 * q)
-    pz2 = r(-2 * t2 * ab12 * a12 + 4 * q * a12)
+    zb1p = r(s12 * ab12 + 2 * t2 * q)
+    pz2 = r(a12 * (q - 2 * t2 * ab12))
     tr.update(za1=za1, zb1p=zb1p, pz2=pz2)
     # P4 / E5
     aa1, ab11 = za1 @ W1.T, zb1p @ W1.T
     dW1 = a11.T @ zb1p
     za0 = r(aa1 * s11)
     q = aa1 * a11
-    zb1pp = r(s11 * ab11 + 8 * t1 * q)
-    pz1 = r(-2 * t1 * ab11 * a11 + 4 * q * a11)
+    zb1pp = r(s11 * ab11 + 2 * t1 * q)
+    pz1 = r(a11 * (q - 2 * t1 * ab11))
     tr.update(za0=za0, zb1pp=zb1pp, pz1=pz1)
     # P5 / E6
-    g = za0 @ W0.T
+    g = 0.25 * (za0 @ W0.T)
     dW0 = v.T @ zb1pp
-    gt = r(2 * g)
+    gt = r(0.5 * g)                          # g^ = g / 2
     tr.update(g=g)
     # P6 / E7
     zg0 = gt @ W0
@@ -84,7 +84,7 @@ def kfp_0T_schedule(W, b, x, v, gamma: float, weight: float, mask=None, emulate_
     tr.update(c_1=c1, c_2=c2)
     # P8 / E9
     ug = ag2 @ W2
-    s0f = s0p + 2 * ug
+    s0f = s0p + 8 * ug
     db2 = s0f.sum(0)
     s0 = r(s0f)
     tr.update(s0=s0)

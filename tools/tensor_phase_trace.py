@@ -1,33 +1,45 @@
-import sys, ctypes as C, torch
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pde_inverse_problem_b200 import ops, _lib as L
-from oracle import model as o_model
+"""Per-phase clock trace of the tcgen05 residual kernel (build csrc with EXTRA=-DPDEIP_TC_TRACE first)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import model as o_model  # noqa: E402
+from pde_inverse_problem_b200 import _lib as L, ops  # noqa: E402
+
 cuda = torch.device('cuda')
-d=8; n=(1<<18)*200
+d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+n = (1 << 18) * 200
 p = o_model.init_mlp_params(d, 32, 2)
 flat = o_model.flatten_params(p).float().to(cuda)
-pts = torch.randn(2*d, n, device=cuda)
-TG = ops.TrueGrad(L.DRIFT_GMM, (torch.rand(16, d, device=cuda)*8-4), 1.0)
+pts = torch.randn(3 * d, n, device=cuda)
 spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
 acc = ops.ResidualAccumulator(spec, device=cuda).begin()
-import time
+tg = ops.TrueGrad(L.DRIFT_IN_POINTS)
 for _ in range(2):
-    acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0/n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=TG)
+    acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=tg)
 torch.cuda.synchronize()
 lib = C.CDLL(L.LIB_PATH)
-lib.pdeip_debug_tensor_trace.argtypes=[C.c_void_p, C.c_int]
-buf = (C.c_longlong*64)()
-print(lib.pdeip_debug_tensor_trace(buf, 64))
+lib.pdeip_debug_tensor_trace.argtypes = [C.c_void_p, C.c_int]
+buf = (C.c_longlong * 192)()
+print("rc", lib.pdeip_debug_tensor_trace(buf, 192))
 t = list(buf)
 t0 = t[0]
-print("phase: t_arrive(rel)  arrive->mma_start  mma_start->issued  issued->done   total")
+print("ph s | wait_start wait_end arrive | mma_ready fast_issued all_issued   (cycles since E0(s0) wait start)")
 for ph in range(12):
-    a, b, c_, dn = t[4*ph:4*ph+4]
-    print(ph, a-t0, b-a, c_-b, dn-c_, " total", dn-a)
-print("tile start->S0 arrive", t[0]-t[60], " tile total", t[61]-t[60])
-ntile = (n + 127)//128
-per_cta = ntile/148
-print("CTA0 loop cycles", t[63]-t[62], "tiles/CTA", per_cta, "cycles/tile", (t[63]-t[62])/per_cta)
-e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
-e0.record(); acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0/n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=TG); e1.record(); torch.cuda.synchronize()
-print("kernel ms", e0.elapsed_time(e1), "evals/s", n/e0.elapsed_time(e1)*1e3)
+    for s in range(2):
+        r = t[(ph * 2 + s) * 8:(ph * 2 + s) * 8 + 8]
+        if r[0] == 0:
+            continue
+        print(ph, s, "|", r[0] - t0, r[1] - t0, r[2] - t0, "|", r[4] - t0, r[5] - t0 if r[5] else '-', r[6] - t0,
+              "   wait", r[1] - r[0], "epi", r[2] - r[1])
+e0 = torch.cuda.Event(enable_timing=True)
+e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=tg)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+print("kernel ms", ms, "evals/s", n / ms * 1e3, "cycles/tile @1.965GHz", ms * 1e-3 * 1.965e9 / (n / 128 / 148))
