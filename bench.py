@@ -248,12 +248,21 @@ def run_ours(args):
         flop_eval = 24 * m1(d)
         res_rate = n * hp.s_emit / t_res  # per GPU
         res_tflops = res_rate * flop_eval / 1e12
+        # DRAM bytes per residual launch: ncu --set full of this kernel (profiles/r01_summary_tensor_v2.md) measured
+        # 96.6 B per point at d = 8 (96 B algorithmic: x, v, grad U): scaled to this run's points per launch
+        pts_launch = cfg.chunk * hp.s_emit
+        if path == L.PATH_TENSOR and d == 8:
+            res_traffic = 96.6 * pts_launch
+            res_traffic_src = "ncu dram__bytes_read+write per point (65 536-particle capture) x points per launch"
+        else:
+            res_traffic, res_traffic_src = None, "not captured for this configuration"
         int_rate = n * (S + 1) / t_int
         int_gbs = n * hp.s_emit * 3 * d * 4 / t_int / 1e9  # [x, v, grad U(x)] per emitted sample
         line = {
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": shard.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if path == L.PATH_FP32 else "tf32/bf16+f32",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if path == L.PATH_FP32 else "bf16 GEMM operands (weights and x split hi+lo), f32 accumulate / epilogue / integrator",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
                        "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
@@ -268,7 +277,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": "mlp_residual_kernel (KFP 0T)", "bound": "tensor", "achieved": res_tflops,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
-                         "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                         "traffic": res_traffic, "traffic_source": res_traffic_src,
+                         "peak_source": pk["src"] + " bf16 sustained",
                          "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval},
             "kernels": {
                 "kl_integrate": {"bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
@@ -367,7 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default=os.environ.get("PDEIP_BENCH_PATH", "fp32"), choices=["fp32", "tensor"])
+    ap.add_argument("--path", default=os.environ.get("PDEIP_BENCH_PATH", "tensor"), choices=["fp32", "tensor"],
+                    help="residual kernel: tensor = tcgen05 bf16 GEMM path (rtol 1e-2, default), fp32 = CUDA-core parity path (rtol 1e-5)")
     ap.add_argument("--particles", type=int, default=0, help="override particles per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

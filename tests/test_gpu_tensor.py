@@ -35,7 +35,7 @@ def _run(ops, L, cuda, spec, flat, pts, n, gamma, tg, path, layout=None):
     return s, g
 
 
-@pytest.mark.parametrize("d,n", [(4, 128), (8, 1000), (16, 300), (2, 77)])
+@pytest.mark.parametrize("d,n", [(4, 128), (8, 1000), (16, 300), (2, 77), (32, 500), (8, 40000), (24, 129)])
 def test_tensor_path_matches_oracle(cuda, d, n):
     ops, L = _ops()
     pde = o_prob.KineticOUProblem(d, T=2.0)

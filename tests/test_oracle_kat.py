@@ -313,3 +313,60 @@ def _unflatten(flat, d, hidden=32, layers=2):
                                "bias": flat[off + nw:off + nw + dims[i + 1]]}
         off += nw + dims[i + 1]
     return {"params": tree}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# phase schedule of the tcgen05 residual kernel (tests/tensor_v2_model.py) against the hand-derived Taylor twin
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [2, 8, 16, 32])
+def test_tensor_kernel_schedule_matches_taylor_oracle(d):
+    """The kernel's rescaled streams (a2^ = -a2/2, g^ = g/2, za^ = 4 za), the adjoints taken from the input-gradient
+    chain, the pz terms and the merged band c = a2^ + ag^ are algebraically identical to SURVEY §9 (float64)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from tensor_v2_model import kfp_0T_schedule
+    from oracle import taylor as o_tay, model as o_model
+    g = torch.Generator().manual_seed(40 + d)
+    p = o_model.init_mlp_params(d, 32, 2, seed=d)
+    for k in p["params"]:
+        b = p["params"][k]["bias"]
+        p["params"][k]["bias"] = 0.1 * torch.randn(b.shape, generator=g, dtype=torch.float64)
+    W, b = o_tay.unpack(p)
+    n, gamma = 300, 0.7
+    z = torch.randn(n, 2 * d, generator=g, dtype=torch.float64)
+    val, dW, db, _, gvec = o_tay.point_set(W, b, z[:, :d], [(z[:, d:], -2.0, 2.0 * gamma)], 0.0, 1.0, 1.0 / n)
+    r = kfp_0T_schedule(W, b, z[:, :d], z[:, d:], gamma, 1.0 / n)
+    assert abs(float(val) - float(r["loss"])) <= 1e-12 * abs(float(val))
+    assert (gvec - r["g"]).abs().max() <= 1e-12 * gvec.abs().max()
+    for l in range(3):
+        assert (dW[l] - r["dW"][l]).abs().max() <= 1e-12 * dW[l].abs().max()
+        assert (db[l] - r["db"][l]).abs().max() <= 1e-12 * db[l].abs().max()
+    # masked tail points contribute nothing
+    mask = (torch.arange(n) < n - 37).double()
+    rm = kfp_0T_schedule(W, b, z[:, :d], z[:, d:], gamma, 1.0 / n, mask=mask)
+    rs = kfp_0T_schedule(W, b, z[: n - 37, :d], z[: n - 37, d:], gamma, 1.0 / n)
+    assert abs(float(rm["loss"]) - float(rs["loss"])) <= 1e-12 * abs(float(rs["loss"]))
+    for l in range(3):
+        assert (rm["dW"][l] - rs["dW"][l]).abs().max() <= 1e-12 * rs["dW"][l].abs().max()
+        assert (rm["db"][l] - rs["db"][l]).abs().max() <= 1e-12 * rs["db"][l].abs().max()
+
+
+def test_tensor_kernel_schedule_bf16_emulation_within_tolerance():
+    """With every operand rounded to bf16 where the kernel rounds it, the schedule stays within the 1e-2 tolerance of
+    BASELINE.json for the bf16 GEMM path (per-tensor max-norm metric)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from tensor_v2_model import kfp_0T_schedule
+    from oracle import taylor as o_tay, model as o_model
+    d, n, gamma = 8, 20000, 0.5
+    g = torch.Generator().manual_seed(3)
+    p = o_model.init_mlp_params(d, 32, 2, seed=3)
+    W, b = o_tay.unpack(p)
+    scale = torch.cat([torch.full((d,), 2.0), torch.full((d,), 0.6)]).double()
+    z = torch.randn(n, 2 * d, generator=g, dtype=torch.float64) * scale
+    val, dW, db, _, _ = o_tay.point_set(W, b, z[:, :d], [(z[:, d:], -2.0, 2.0 * gamma)], 0.0, 1.0, 1.0 / n)
+    r = kfp_0T_schedule(W, b, z[:, :d], z[:, d:], gamma, 1.0 / n, emulate_bf16=True)
+    ref = torch.cat([torch.cat([w_.reshape(-1), b_.reshape(-1)]) for w_, b_ in zip(dW, db)])
+    got = torch.cat([torch.cat([w_.reshape(-1), b_.reshape(-1)]) for w_, b_ in zip(r["dW"], r["db"])])
+    assert abs(float(val) - float(r["loss"])) < 1e-2 * abs(float(val))
+    assert (ref - got).abs().max() < 1e-2 * ref.abs().max()
