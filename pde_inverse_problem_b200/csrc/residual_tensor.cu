@@ -161,11 +161,12 @@ __device__ __forceinline__ void mm_fwd(const uint32_t (&d)[NG], Desc a, const ui
   for (int k = 0; k < K; k += 16)
 #pragma unroll
     for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi, k * 16, idesc, k > 0 ? 1u : 0u);
-  if constexpr (!LO) return;
+  if constexpr (LO) {
 #pragma unroll
-  for (int k = 0; k < K; k += 16)
+    for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
+      for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
+  }
 }
 // NG backward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W (transposed view of the weight tile, rows = K)
 template <int K, int N, int NG, bool LO = true>
@@ -176,11 +177,12 @@ __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const ui
   for (int k = 0; k < K; k += 16)
 #pragma unroll
     for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_hi_m, (k >> 3) * w_rg, idesc, k > 0 ? 1u : 0u);
-  if constexpr (!LO) return;
+  if constexpr (LO) {
 #pragma unroll
-  for (int k = 0; k < K; k += 16)
+    for (int k = 0; k < K; k += 16)
 #pragma unroll
-    for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo_m, (k >> 3) * w_rg, idesc, 1u);
+      for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo_m, (k >> 3) * w_rg, idesc, 1u);
+  }
 }
 // band-shifted batch-reduced outer product: D[m][n] += sum_points A[p][a_col0 + m] * B[p][b_col0 + n]
 // (both operands transposed views; a_off / b_off = byte offsets of the first chunk of the band)
@@ -442,11 +444,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
           const uint32_t mb = smem_u32(mbar_p + s);
           const Desc XK = mk_desc(sb + S::O_X, 128, S::RG_X), A1K = mk_desc(sb + S::O_A1, 128, S::RG_A),
                      A2K = mk_desc(sb + S::O_A2, 128, S::RG_A), ZK = mk_desc(sb + S::O_Z, 128, S::RG_Z);
-          const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), A1M = mk_desc(sb + S::O_A1, S::RG_A, 128),
-                     A2M = mk_desc(sb + S::O_A2, S::RG_A, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
-          const uint32_t acc_first = (dw_started | (uint32_t)s) ? 1u : 0u;
+          const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
+          TC_TRACE_DECL_MMA;
           mma_wait_operands(s);
           if (elect_one()) {
+            TC_TRACE(4);
             switch (ph) {
               case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
                 mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
@@ -464,17 +466,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
               case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
                 mm_bwd<OP, 32, 2>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
-                mm_outer<OP>(TB + C_DW2, A2M, AC_A1 * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, acc_first);
               } break;
               case 4: {  // aa1 = za1 W1^T, ab1_1 = zbar1' W1^T;  dW1 += a1_1^T zbar1'
                 mm_bwd<32, 32, 2>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
-                mm_outer<32>(TB + C_DW1, A1M, AC_A1 * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, acc_first);
               } break;
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
                 mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
                 commit(mb);
-                mm_outer<32>(TB + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
               } break;
               case 6: {  // zg^_0 = g^ W0
                 mm_fwd<S::KV, 32, 1, false>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
@@ -491,14 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
                 mm_bwd<OP, 32, 2, false>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
-                mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
-                mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
               } break;
               case 10: {  // ab_1 = zbar0' W1^T, aa1 again;  dW1 += t1^T zbar0' + c_1^T za1
                 mm_bwd<32, 32, 2, false>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
-                mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
-                mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
               } break;
               default: {  // dW0 += x_hi^T zbar0'' + x_lo^T zbar0'' + g^^T za0
                 mm_outer<32>(TB + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
@@ -507,8 +502,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
                 commit(mb);  // the next tile's E0 overwrites the x | v bands
               } break;
             }
+            TC_TRACE(6);
           }
           __syncwarp();
+        }
+        // background (batch-reduced dW) GEMMs of this phase, issued after the fast GEMMs of BOTH slots so that the
+        // second slot's fast GEMMs do not queue behind the first slot's dW chains (the tensor pipe runs in issue order)
+        if (ph == 3 || ph == 4 || ph == 5 || ph == 9 || ph == 10) {
+#pragma unroll 1
+          for (int s = 0; s < NS; ++s) {
+            const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
+            const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), A1M = mk_desc(sb + S::O_A1, S::RG_A, 128),
+                       A2M = mk_desc(sb + S::O_A2, S::RG_A, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
+            const uint32_t acc_first = (dw_started | (uint32_t)s) ? 1u : 0u;
+            if (elect_one()) {
+              switch (ph) {
+                case 3:  // dW2 += a1_2^T s1v
+                  mm_outer<OP>(TB + C_DW2, A2M, AC_A1 * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+                  break;
+                case 4:  // dW1 += a1_1^T zbar1'
+                  mm_outer<32>(TB + C_DW1, A1M, AC_A1 * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, acc_first);
+                  break;
+                case 5:  // dW0 += v^T zbar1''
+                  mm_outer<32>(TB + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+                  break;
+                case 9:  // dW2 += t2^T s0 + c_2^T za2
+                  mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                  mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+                  break;
+                default:  // dW1 += t1^T zbar0' + c_1^T za1
+                  mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
+                  mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+                  break;
+              }
+            }
+            __syncwarp();
+          }
         }
       }
       dw_started = 1u;
@@ -581,14 +610,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 #ifdef PDEIP_TC_PROBE
       const bool probe_on = blockIdx.x == 0 && tile == 0;
 #endif
+#ifdef PDEIP_TC_TRACE
+      long long* trace = reinterpret_cast<long long*>(status) + 512;
+      const bool trace_on = blockIdx.x == 0 && tid == 0 && base == (int64_t)50 * tile_stride;
+#endif
+      TC_TRACE(0);
       if (!(ph == 0 && first)) {  // GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
         if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
           ok = false;
           atomicExch(status, 1);
         }
         par[s] ^= 1u;
+        TC_TRACE(3);
         fence_after_sync();
       }
+      TC_TRACE(1);
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
@@ -794,6 +830,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       } else {
         // E10: zbar0' = s1_2 ab_2 + pz2 - 2 t2 aa^2 c_2;  db1       E11: zbar0'' likewise with hidden layer 1;  db0
         constexpr bool l2 = ph == 10;
+        // next tile of this slot: issue the input loads first, so that the DRAM latency overlaps this phase's work (the
+        // proxy fence of epi_arrive waits for every outstanding load of the thread: a load issued late in a phase is a
+        // blocking load)
+        if constexpr (l2) load_inputs(Sc, tile + tile_stride);
         const uint8_t* At = l2 ? A2 : A1;
         float ab[16], aa[16], t[16], cc[16];
         uint32_t s1p[8], pzp[8];
@@ -818,10 +858,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 #pragma unroll
         for (int c = 0; c < 2; ++c) put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
         TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
-        // prefetch the next tile of this slot while its last GEMMs run
-        if constexpr (!l2) load_inputs(Sc, tile + tile_stride);
       }
+      TC_TRACE(7);
       epi_arrive(s);
+      TC_TRACE(2);
     };
 #define PDEIP_TC_PHASE(PH)                       \
   phase(IC<PH>{}, IC<0>{});                      \

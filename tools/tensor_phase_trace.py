@@ -34,7 +34,8 @@ for ph in range(12):
         if r[0] == 0:
             continue
         print(ph, s, "|", r[0] - t0, r[1] - t0, r[2] - t0, "|", r[4] - t0, r[5] - t0 if r[5] else '-', r[6] - t0,
-              "   wait", r[1] - r[0], "epi", r[2] - r[1])
+              "   wait", r[1] - r[0], "(mbar", (r[3] - r[0]) if r[3] else '-', ") epi", r[2] - r[1],
+              "(arrive", (r[2] - r[7]) if r[7] else '-', ")")
 e0 = torch.cuda.Event(enable_timing=True)
 e1 = torch.cuda.Event(enable_timing=True)
 e0.record()
