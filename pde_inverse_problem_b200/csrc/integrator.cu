@@ -9,6 +9,8 @@
 #include "drift.cuh"
 #include "philox.cuh"
 
+#include <stdlib.h>
+
 namespace pdeip {
 
 struct IntegrateArgs {
@@ -214,8 +216,218 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Production configuration of K1 (pipeline.HotPath): in-register Philox noise, per-particle tau0, every sample
+// emitted as [x, v, grad U(x)] into the [3d][S][N] SoA trajectory, d == DP.  Same arithmetic as the generic kernel
+// above up to rounding: the GMM drift is a branch-free tiled online softmax (8 centres per tile, one rescale per
+// tile) on MUFU ex2, and every d-wide loop runs on packed fp32x2 instructions (FFMA2: half the issue slots).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int kGmmTile = 8;  // centres per softmax tile; the centre table is padded to a multiple with far-away rows
+
+// mus_s: smem [Kpad][DP]; c2 = -0.5 * inv_sigma2 * log2(e).  g = (x - sum_k softmax_k mu_k) * inv_sigma2
+template <int DP>
+__device__ __forceinline__ void gmm_grad_fast(const float2 (&x)[DP / 2], const float* __restrict__ mus_s, int k_pad, float c2,
+                                              float inv_sigma2, float2 (&g)[DP / 2]) {
+  float m = -INFINITY, se = 0.f;
+  float2 acc[DP / 2];
+#pragma unroll
+  for (int i = 0; i < DP / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+  const float2 neg1 = make_float2(-1.f, -1.f);
+#pragma unroll 1
+  for (int k0 = 0; k0 < k_pad; k0 += kGmmTile) {
+    float al[kGmmTile];
+#pragma unroll
+    for (int kk = 0; kk < kGmmTile; ++kk) {
+      const float4* mu4 = reinterpret_cast<const float4*>(mus_s + (k0 + kk) * DP);
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i4 = 0; i4 < DP / 4; ++i4) {
+        const float4 t = mu4[i4];
+        const float2 r0 = __ffma2_rn(make_float2(t.x, t.y), neg1, x[2 * i4]);
+        const float2 r1 = __ffma2_rn(make_float2(t.z, t.w), neg1, x[2 * i4 + 1]);
+        s2 = __ffma2_rn(r0, r0, s2);
+        s2 = __ffma2_rn(r1, r1, s2);
+      }
+      al[kk] = c2 * (s2.x + s2.y);  // log2 of the unnormalised weight
+    }
+    float tm = al[0];
+#pragma unroll
+    for (int kk = 1; kk < kGmmTile; ++kk) tm = fmaxf(tm, al[kk]);
+    const float mn = fmaxf(m, tm);
+    const float sc = ex2_approx(m - mn);  // m = -inf on the first tile: ex2(-inf) = 0 and acc, se are 0 anyway
+    m = mn;
+    se *= sc;
+    const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+    for (int i = 0; i < DP / 2; ++i) acc[i] = __fmul2_rn(acc[i], sc2);
+#pragma unroll
+    for (int kk = 0; kk < kGmmTile; ++kk) {
+      const float e = ex2_approx(al[kk] - m);
+      se += e;
+      const float2 e2 = make_float2(e, e);
+      const float4* mu4 = reinterpret_cast<const float4*>(mus_s + (k0 + kk) * DP);
+#pragma unroll
+      for (int i4 = 0; i4 < DP / 4; ++i4) {
+        const float4 t = mu4[i4];
+        acc[2 * i4] = __ffma2_rn(e2, make_float2(t.x, t.y), acc[2 * i4]);
+        acc[2 * i4 + 1] = __ffma2_rn(e2, make_float2(t.z, t.w), acc[2 * i4 + 1]);
+      }
+    }
+  }
+  const float ninv = -1.f / se;
+  const float2 ninv2 = make_float2(ninv, ninv), is2 = make_float2(inv_sigma2, inv_sigma2);
+#pragma unroll
+  for (int i = 0; i < DP / 2; ++i) g[i] = __fmul2_rn(__ffma2_rn(acc[i], ninv2, x[i]), is2);
+}
+
+// AT_s: smem [DP][DP], AT_s[k][i] = A[i][k];  g = A x
+template <int DP>
+__device__ __forceinline__ void linear_grad_fast(const float2 (&x)[DP / 2], const float* __restrict__ AT_s, float2 (&g)[DP / 2]) {
+#pragma unroll
+  for (int i = 0; i < DP / 2; ++i) g[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < DP; ++k) {
+    const float xk = (k & 1) ? x[k >> 1].y : x[k >> 1].x;
+    const float2 xk2 = make_float2(xk, xk);
+    const float4* row = reinterpret_cast<const float4*>(AT_s + k * DP);
+#pragma unroll
+    for (int i4 = 0; i4 < DP / 4; ++i4) {
+      const float4 t = row[i4];
+      g[2 * i4] = __ffma2_rn(make_float2(t.x, t.y), xk2, g[2 * i4]);
+      g[2 * i4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xk2, g[2 * i4 + 1]);
+    }
+  }
+}
+
+#ifndef PDEIP_FAST_MINB
+#define PDEIP_FAST_MINB 4
+#endif
+template <int DP, int DRIFT>
+__global__ void __launch_bounds__(128, PDEIP_FAST_MINB) kl_integrate_fast_kernel(const IntegrateArgs a, int k_pad) {
+  static_assert(DP % 4 == 0, "packed path needs d % 4 == 0");
+  extern __shared__ __align__(16) float smem[];
+  if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
+    for (int idx = threadIdx.x; idx < k_pad * DP; idx += blockDim.x) {
+      const int r = idx / DP;
+      smem[idx] = r < a.n_gaussian ? a.drift_params[idx] : 1.0e18f;  // padding rows: weight exactly 0
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < DP * DP; idx += blockDim.x) {
+      const int k = idx / DP, i = idx - k * DP;
+      smem[idx] = a.drift_params[i * DP + k];
+    }
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n) return;
+  const uint64_t pid = a.particle_offset + (uint64_t)n;
+  float2 q[DP / 2], p[DP / 2];
+  {
+    const float4* z4 = reinterpret_cast<const float4*>(a.z0 + n * (2 * DP));
+#pragma unroll
+    for (int i4 = 0; i4 < DP / 4; ++i4) {
+      const float4 tq = z4[i4], tp = z4[DP / 4 + i4];
+      q[2 * i4] = make_float2(tq.x, tq.y); q[2 * i4 + 1] = make_float2(tq.z, tq.w);
+      p[2 * i4] = make_float2(tp.x, tp.y); p[2 * i4 + 1] = make_float2(tp.z, tp.w);
+    }
+  }
+  const float t0 = philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
+  const float c2 = -0.5f * a.inv_sigma2 * 1.4426950408889634f;
+  const int S = a.n_steps;
+  const int64_t plane = (int64_t)S * a.n;  // floats per component plane of the [3d][S][N] trajectory
+  float* o = a.traj + n;                   // sample 0, component 0 of this particle
+#pragma unroll 1
+  for (int s = 0; s <= S; ++s) {
+    const float h = (s == 0) ? t0 : ((s == S) ? a.dt - t0 : a.dt);  // sampling_utils.py:33,45-46
+    float2 g[DP / 2];
+    if constexpr (DRIFT == PDEIP_DRIFT_GMM) gmm_grad_fast<DP>(q, smem, k_pad, c2, a.inv_sigma2, g);
+    else linear_grad_fast<DP>(q, smem, g);
+    if (s >= 1) {  // grad U at the state emitted as sample s - 1
+      float* og = o - a.n + 2 * DP * plane;
+#pragma unroll
+      for (int i = 0; i < DP / 2; ++i) {
+        __stcs(og + (int64_t)(2 * i) * plane, g[i].x);
+        __stcs(og + (int64_t)(2 * i + 1) * plane, g[i].y);
+      }
+    }
+    // p' = p - h g + sqrt(2 h) xi - gamma h p ;  q' = q + h p'     (sampling_utils.py:14-20)
+    const float sq = sqrtf(h) * 1.41421356237309515f;
+    const float2 sq2 = make_float2(sq, sq), nh2 = make_float2(-h, -h), h2 = make_float2(h, h);
+    const float dmp = 1.f - a.gamma * h;
+    const float2 dmp2 = make_float2(dmp, dmp);
+#pragma unroll
+    for (int j = 0; j < DP / 4; ++j) {
+      float r4[4];
+      philox_normal4(a.seed, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
+      const float2 xa = make_float2(r4[0], r4[1]), xb = make_float2(r4[2], r4[3]);
+      // same association as the generic kernel up to the fused damping factor (1 - gamma h)
+      float2 pa = __ffma2_rn(nh2, g[2 * j], __fmul2_rn(p[2 * j], dmp2));
+      float2 pb = __ffma2_rn(nh2, g[2 * j + 1], __fmul2_rn(p[2 * j + 1], dmp2));
+      pa = __ffma2_rn(sq2, xa, pa);
+      pb = __ffma2_rn(sq2, xb, pb);
+      p[2 * j] = pa; p[2 * j + 1] = pb;
+      q[2 * j] = __ffma2_rn(h2, pa, q[2 * j]);
+      q[2 * j + 1] = __ffma2_rn(h2, pb, q[2 * j + 1]);
+    }
+    if (s < S) {
+#pragma unroll
+      for (int i = 0; i < DP / 2; ++i) {
+        __stcs(o + (int64_t)(2 * i) * plane, q[i].x);
+        __stcs(o + (int64_t)(2 * i + 1) * plane, q[i].y);
+        __stcs(o + (int64_t)(DP + 2 * i) * plane, p[i].x);
+        __stcs(o + (int64_t)(DP + 2 * i + 1) * plane, p[i].y);
+      }
+      o += a.n;
+    }
+  }
+  {
+    float4* zl = reinterpret_cast<float4*>(a.z_last + n * (2 * DP));
+#pragma unroll
+    for (int i4 = 0; i4 < DP / 4; ++i4) {
+      zl[i4] = make_float4(q[2 * i4].x, q[2 * i4].y, q[2 * i4 + 1].x, q[2 * i4 + 1].y);
+      zl[DP / 4 + i4] = make_float4(p[2 * i4].x, p[2 * i4].y, p[2 * i4 + 1].x, p[2 * i4 + 1].y);
+    }
+  }
+}
+
+// true if the call is the production configuration served by kl_integrate_fast_kernel
+static bool fast_path_ok(const IntegrateArgs& a, int drift_kind, int DP) {
+  // DP = 32 keeps five 32-wide register arrays live and spills: the generic kernel is faster there
+  return a.d == DP && DP % 4 == 0 && DP <= 16 && (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR) && !a.noise &&
+         !a.tau0 && !a.tau && a.traj && a.z_last && a.emit_drift && a.emit_every == 1 && a.emit_offset == 0 &&
+         a.schedule == PDEIP_SCHEDULE_REFERENCE && a.state_layout == PDEIP_LAYOUT_AOS &&
+         a.traj_layout == PDEIP_TRAJ_TIME_SOA && getenv("PDEIP_NO_FAST_INTEGRATOR") == nullptr;
+}
+
+template <int DP>
+static int launch_integrate_fast(const IntegrateArgs& a, int drift_kind, cudaStream_t st) {
+  if constexpr (DP % 4 == 0) {
+    const int block = 128;
+    const int64_t grid = (a.n + block - 1) / block;
+    if (drift_kind == PDEIP_DRIFT_GMM) {
+      const int k_pad = (a.n_gaussian + kGmmTile - 1) / kGmmTile * kGmmTile;
+      const size_t smem = sizeof(float) * (size_t)k_pad * DP;
+      PDEIP_REQUIRE(smem <= 48 * 1024, PDEIP_ERR_UNSUPPORTED, "GMM centres exceed 48 KB of shared memory");
+      kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
+    } else {
+      kl_integrate_fast_kernel<DP, PDEIP_DRIFT_LINEAR><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
+    }
+    PDEIP_LAUNCH_OK();
+    return PDEIP_OK;
+  } else {
+    return PDEIP_ERR_UNSUPPORTED;
+  }
+}
+
 template <int DP>
 static int launch_integrate(const IntegrateArgs& a, int drift_kind, cudaStream_t st) {
+  if (fast_path_ok(a, drift_kind, DP)) return launch_integrate_fast<DP>(a, drift_kind, st);
   const int block = 128;
   const int64_t grid = (a.n + block - 1) / block;
   size_t smem = 0;
