@@ -615,6 +615,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       const bool trace_on = blockIdx.x == 0 && tid == 0 && base == (int64_t)50 * tile_stride;
 #endif
       TC_TRACE(0);
+#ifdef PDEIP_TC_TRACE
+      if (trace_on && !(ph == 0 && first)) {  // latency and outcome of the first poll
+        const long long ta = clock64();
+        const bool hit = mbar_try_wait(smem_u32(mbar_p + s), par[s]);
+        const long long tb = clock64();
+        trace[192 + (ph * 2 + s) * 2] = tb - ta;
+        trace[192 + (ph * 2 + s) * 2 + 1] = hit ? 1 : 0;
+      }
+#endif
       if (!(ph == 0 && first)) {  // GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
         if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
           ok = false;
@@ -1015,7 +1024,7 @@ extern "C" int pdeip_tensor_path_status(void* stream, int* out_status) {
 extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
   int* status = pdeip::tensor_status_word();
   if (!status) return PDEIP_ERR_CUDA;
-  if (n > 24 * 8) return PDEIP_ERR_INVALID_ARG;
+  if (n > 24 * 8 + 48) return PDEIP_ERR_INVALID_ARG;
   if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
   if (cudaMemcpy(out, reinterpret_cast<long long*>(status) + 512, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost) !=
       cudaSuccess)
