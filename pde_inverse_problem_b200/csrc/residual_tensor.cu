@@ -547,9 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     // epilogue warps
     // ========================================================================================================
     bool ok = true;
-    uint32_t par[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) par[s] = 0;
+    uint32_t par = 0;  // bit s = parity of slot s's mbarrier
 #ifdef PDEIP_TC_PROBE
     float* probe = reinterpret_cast<float*>(status) + 2048;
 #endif
@@ -570,9 +568,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     const int u16 = 16 * half, u24 = 24 * half;  // first unit owned in 32- / 48-unit tiles
     // prefetched input chunks: item j = half + 2 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
     constexpr int NI = (3 * S::XC + 1) / 2;
-    float xin[NS][NI][8];
-    auto load_inputs = [&](auto Sc, int64_t t) {
-      constexpr int s = decltype(Sc)::value;
+    float xin0[NI][8], xin1[NI][8];
+    auto load_into = [&](float (&xin)[NI][8], int64_t t) {
       const int64_t pp = t * 128 + row;
       const int64_t pc = (t < n_tiles && pp < a.n_points) ? pp : 0;
 #pragma unroll
@@ -584,20 +581,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
         for (int e = 0; e < 8; ++e) {
           const int u = cg * 8 + e;
           const int uc = u < d ? u : 0;
-          xin[s][i][e] = __ldg(a.points + elem_index(a.layout, pc, bandc * d + uc, a.n_points, dimw));
+          xin[i][e] = __ldg(a.points + elem_index(a.layout, pc, bandc * d + uc, a.n_points, dimw));
         }
       }
     };
-    load_inputs(IC<0>{}, (int64_t)blockIdx.x * NS);
-    if constexpr (NS == 2) load_inputs(IC<1>{}, (int64_t)blockIdx.x * NS + 1);
+    // two separate branches: each slot's loads target its own registers directly (no select on the loaded value)
+    auto load_inputs = [&](int s, int64_t t) {
+      if (NS == 2 && s == 1) load_into(xin1, t);
+      else load_into(xin0, t);
+    };
+    load_inputs(0, (int64_t)blockIdx.x * NS);
+    if constexpr (NS == 2) load_inputs(1, (int64_t)blockIdx.x * NS + 1);
 
     bool first = true;
     int64_t base = (int64_t)blockIdx.x * NS;
 
     // one epilogue phase of one slot: wait for the previous GEMM phase of that slot, compute, signal the MMA warp
-    auto phase = [&](auto PHc, auto Sc) {
+    // The phase bodies are shared by the two slots (runtime slot offsets): E_k(slot 0) and E_k(slot 1) run back to
+    // back on the same ~20 KB of instructions, so the second pass is served by the instruction cache.
+    auto phase = [&](auto PHc, const int s) {
       constexpr int ph = decltype(PHc)::value;
-      constexpr int s = decltype(Sc)::value;
       uint8_t* const X = sm + (uint32_t)s * S::SLOT + S::O_X + offX;
       uint8_t* const A1 = sm + (uint32_t)s * S::SLOT + S::O_A1 + offA;
       uint8_t* const A2 = sm + (uint32_t)s * S::SLOT + S::O_A2 + offA;
@@ -618,44 +621,48 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
 #ifdef PDEIP_TC_TRACE
       if (trace_on && !(ph == 0 && first)) {  // latency and outcome of the first poll
         const long long ta = clock64();
-        const bool hit = mbar_try_wait(smem_u32(mbar_p + s), par[s]);
+        const bool hit = mbar_try_wait(smem_u32(mbar_p + s), (par >> s) & 1u);
         const long long tb = clock64();
         trace[192 + (ph * 2 + s) * 2] = tb - ta;
         trace[192 + (ph * 2 + s) * 2 + 1] = hit ? 1 : 0;
       }
 #endif
       if (!(ph == 0 && first)) {  // GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
-        if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
+        if (ok && !mbar_wait(smem_u32(mbar_p + s), (par >> s) & 1u)) {
           ok = false;
           atomicExch(status, 1);
         }
-        par[s] ^= 1u;
+        par ^= 1u << s;
         TC_TRACE(3);
         fence_after_sync();
       }
       TC_TRACE(1);
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
+        auto emit = [&](const float (&xin)[NI][8]) {
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int j = half + 2 * i;
-          const int band = j / S::XC, cg = j % S::XC;
-          if (band == 0) {
-            float hi[8], lo[8];
+          for (int i = 0; i < NI; ++i) {
+            const int j = half + 2 * i;
+            const int band = j / S::XC, cg = j % S::XC;
+            if (band == 0) {
+              float hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float xv = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
-              hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
-              lo[e] = xv - hi[e];
+              for (int e = 0; e < 8; ++e) {
+                const float xv = (valid && cg * 8 + e < d) ? xin[i][e] : 0.f;
+                hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
+                lo[e] = xv - hi[e];
+              }
+              put_chunk(X, (S::XC_HI + cg) * 128, hi);
+              put_chunk(X, (S::XC_LO + cg) * 128, lo);
+            } else if (band == 1) {
+              float vv[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) vv[e] = (valid && cg * 8 + e < d) ? xin[i][e] : 0.f;
+              put_chunk(X, (S::XC_V + cg) * 128, vv);
             }
-            put_chunk(X, (S::XC_HI + cg) * 128, hi);
-            put_chunk(X, (S::XC_LO + cg) * 128, lo);
-          } else if (band == 1) {
-            float vv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) vv[e] = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
-            put_chunk(X, (S::XC_V + cg) * 128, vv);
           }
-        }
+        };
+        if (NS == 2 && s == 1) emit(xin1);
+        else emit(xin0);
       } else if constexpr (ph == 1 || ph == 2) {
         // E1: t1, a1_1 = s1 z1, a2^_1 = t a1 z1      E2: t2, a1_2, a2^_2 = s1 z2^ + t a1 z1     (a2^ = -a2 / 2)
         constexpr bool l1 = ph == 1;
@@ -784,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
             if (own_sum) {
               if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) gt[e] = (valid && cg * 8 + e < d) ? xin[s][i][e] : 0.f;
+                for (int e = 0; e < 8; ++e) gt[e] = (valid && cg * 8 + e < d) ? ((NS == 2 && s == 1) ? xin1[i][e] : xin0[i][e]) : 0.f;
               } else if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
                 true_grad_chunk<DP>(a, tp, valid ? p : (int64_t)-1, dimw, cg, gt);
               }
@@ -842,7 +849,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
         // next tile of this slot: issue the input loads first, so that the DRAM latency overlaps this phase's work (the
         // proxy fence of epi_arrive waits for every outstanding load of the thread: a load issued late in a phase is a
         // blocking load)
-        if constexpr (l2) load_inputs(Sc, tile + tile_stride);
+        if constexpr (l2) load_inputs(s, tile + tile_stride);
         const uint8_t* At = l2 ? A2 : A1;
         float ab[16], aa[16], t[16], cc[16];
         uint32_t s1p[8], pzp[8];
@@ -873,8 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       TC_TRACE(2);
     };
 #define PDEIP_TC_PHASE(PH)                       \
-  phase(IC<PH>{}, IC<0>{});                      \
-  if constexpr (NS == 2) phase(IC<PH>{}, IC<1>{});
+  _Pragma("unroll 1") for (int s_ = 0; s_ < NS; ++s_) phase(IC<PH>{}, s_);
 
 #pragma unroll 1
     for (; base < n_tiles; base += tile_stride) {
@@ -886,11 +892,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     // ---- drain: wait for P11 of the last tile of every slot (covers every MMA issued before it) --------------
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      if (ok && !mbar_wait(smem_u32(mbar_p + s), par[s])) {
+      if (ok && !mbar_wait(smem_u32(mbar_p + s), (par >> s) & 1u)) {
         ok = false;
         atomicExch(status, 1);
       }
-      par[s] ^= 1u;
     }
     fence_after_sync();
     asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");

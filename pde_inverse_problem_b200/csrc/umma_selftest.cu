@@ -96,3 +96,57 @@ extern "C" int pdeip_debug_umma(int mode, const float* A, const float* B, float*
   PDEIP_LAUNCH_OK();
   return PDEIP_OK;
 }
+
+// ---- TMEM read-bandwidth probe: every warp streams `reps` x (4 x tcgen05.ld.32x32b.x16) over its lane quadrant ----
+namespace pdeip {
+__global__ void tmem_bw_kernel(int reps, long long* out) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 512);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t la = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(la + (uint32_t)(((r * 4 + j) * 16) & 511))
+          : "memory");
+      acc ^= v[0] ^ v[15];
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = t1 - t0;
+    out[1] = (long long)reps * 4 * 16 * 128 * (blockDim.x / 32);  // bytes read by the CTA: x16 columns x 32 lanes x 4 B per warp load
+  }
+  if (acc == 0x12345678u) out[2] = acc;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace pdeip
+
+extern "C" int pdeip_debug_tmem_bw(int n_warps, int reps, long long* out_host) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 32) != cudaSuccess) return PDEIP_ERR_CUDA;
+  cudaMemset(d, 0, 32);
+  pdeip::tmem_bw_kernel<<<1, 32 * n_warps>>>(reps, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(d); return PDEIP_ERR_CUDA; }
+  cudaMemcpy(out_host, d, 32, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return PDEIP_OK;
+}
