@@ -228,7 +228,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-constexpr int kGmmTile = 8;  // centres per softmax tile; the centre table is padded to a multiple with far-away rows
+constexpr int kGmmTile = 8;  // centres per softmax tile (4 at d = 32: register pressure); the centre table is padded to a
+                             // multiple of 8 with far-away rows
 
 // mus_s: smem [Kpad][DP]; c2 = -0.5 * inv_sigma2 * log2(e).  g = (x - sum_k softmax_k mu_k) * inv_sigma2
 template <int DP>
@@ -239,11 +240,12 @@ __device__ __forceinline__ void gmm_grad_fast(const float2 (&x)[DP / 2], const f
 #pragma unroll
   for (int i = 0; i < DP / 2; ++i) acc[i] = make_float2(0.f, 0.f);
   const float2 neg1 = make_float2(-1.f, -1.f);
+  constexpr int TK = DP >= 32 ? 4 : kGmmTile;
 #pragma unroll 1
-  for (int k0 = 0; k0 < k_pad; k0 += kGmmTile) {
-    float al[kGmmTile];
+  for (int k0 = 0; k0 < k_pad; k0 += TK) {
+    float al[TK];
 #pragma unroll
-    for (int kk = 0; kk < kGmmTile; ++kk) {
+    for (int kk = 0; kk < TK; ++kk) {
       const float4* mu4 = reinterpret_cast<const float4*>(mus_s + (k0 + kk) * DP);
       float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -258,7 +260,7 @@ __device__ __forceinline__ void gmm_grad_fast(const float2 (&x)[DP / 2], const f
     }
     float tm = al[0];
 #pragma unroll
-    for (int kk = 1; kk < kGmmTile; ++kk) tm = fmaxf(tm, al[kk]);
+    for (int kk = 1; kk < TK; ++kk) tm = fmaxf(tm, al[kk]);
     const float mn = fmaxf(m, tm);
     const float sc = ex2_approx(m - mn);  // m = -inf on the first tile: ex2(-inf) = 0 and acc, se are 0 anyway
     m = mn;
@@ -267,7 +269,7 @@ __device__ __forceinline__ void gmm_grad_fast(const float2 (&x)[DP / 2], const f
 #pragma unroll
     for (int i = 0; i < DP / 2; ++i) acc[i] = __fmul2_rn(acc[i], sc2);
 #pragma unroll
-    for (int kk = 0; kk < kGmmTile; ++kk) {
+    for (int kk = 0; kk < TK; ++kk) {
       const float e = ex2_approx(al[kk] - m);
       se += e;
       const float2 e2 = make_float2(e, e);
@@ -309,7 +311,7 @@ __device__ __forceinline__ void linear_grad_fast(const float2 (&x)[DP / 2], cons
 #define PDEIP_FAST_MINB 4
 #endif
 template <int DP, int DRIFT>
-__global__ void __launch_bounds__(128, PDEIP_FAST_MINB) kl_integrate_fast_kernel(const IntegrateArgs a, int k_pad) {
+__global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integrate_fast_kernel(const IntegrateArgs a, int k_pad) {
   static_assert(DP % 4 == 0, "packed path needs d % 4 == 0");
   extern __shared__ __align__(16) float smem[];
   if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
@@ -398,8 +400,7 @@ __global__ void __launch_bounds__(128, PDEIP_FAST_MINB) kl_integrate_fast_kernel
 
 // true if the call is the production configuration served by kl_integrate_fast_kernel
 static bool fast_path_ok(const IntegrateArgs& a, int drift_kind, int DP) {
-  // DP = 32 keeps five 32-wide register arrays live and spills: the generic kernel is faster there
-  return a.d == DP && DP % 4 == 0 && DP <= 16 && (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR) && !a.noise &&
+  return a.d == DP && DP % 4 == 0 && (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR) && !a.noise &&
          !a.tau0 && !a.tau && a.traj && a.z_last && a.emit_drift && a.emit_every == 1 && a.emit_offset == 0 &&
          a.schedule == PDEIP_SCHEDULE_REFERENCE && a.state_layout == PDEIP_LAYOUT_AOS &&
          a.traj_layout == PDEIP_TRAJ_TIME_SOA && getenv("PDEIP_NO_FAST_INTEGRATOR") == nullptr;
