@@ -6,14 +6,14 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import model as o_model  # noqa: E402
 from pde_inverse_problem_b200 import _lib as L, ops  # noqa: E402
+from pde_inverse_problem_b200.core.model import V_hypothesis  # noqa: E402
 
 cuda = torch.device('cuda')
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n = (1 << 18) * 200
-p = o_model.init_mlp_params(d, 32, 2)
-flat = o_model.flatten_params(p).float().to(cuda)
+model = V_hypothesis(1, [32, 32], d)
+flat = model.flat(model.init(11, torch.zeros(d, device=cuda)))
 pts = torch.randn(3 * d, n, device=cuda)
 spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
 acc = ops.ResidualAccumulator(spec, device=cuda).begin()
