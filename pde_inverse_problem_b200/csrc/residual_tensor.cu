@@ -84,8 +84,19 @@ struct Cfg {
   static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
 };
 
+#ifndef PDEIP_TC_LO_FWD
+#define PDEIP_TC_LO_FWD true  // lo halves of W1, W2 in the forward layer GEMMs P1, P2
+#endif
 constexpr int kEpiThreads = 256;            // 8 epilogue warps: thread = (point row, 16-unit half of a 32-unit tile)
-constexpr int kThreads = kEpiThreads + 32;  // + one MMA-issuing warp
+constexpr int kThreads = kEpiThreads + 32;  // + one MMA-issuing warp (threads taking part in the named barriers)
+// Launched with a full third warpgroup (three idle warps) so that `setmaxnreg` can move registers: the register file
+// is 16 K per scheduler and each scheduler hosts two epilogue warps and one warp of the third group; the kernel is
+// compiled for 168 registers, the third group shrinks to 24 and the epilogue groups grow to 232 (no spills).
+constexpr int kLaunchThreads = 384;
+#ifndef PDEIP_TC_REGS2
+#define PDEIP_TC_REGS2 168  // measured: growing the two-slot kernel past 168 registers is slower (1.95e9 vs 2.38e9 evals/s)
+#endif
+constexpr int kRegsEpi = 232, kRegsEpi2 = PDEIP_TC_REGS2, kRegsMma = 24;  // kRegsEpi2: two-slot kernel
 
 template <int V>
 struct IC {
@@ -96,11 +107,13 @@ struct IC {
 // k = 0 epilogue wait start, 1 wait end, 2 arrive;  4 MMA warp operands ready, 5 fast GEMMs issued, 6 all issued
 #ifdef PDEIP_TC_TRACE
 #define TC_TRACE(k) do { if (trace_on) trace[(ph * 2 + s) * 8 + (k)] = clock64(); } while (0)
+#define TC_FINE(k) do { if (trace_on && ph == 4) trace[240 + s * 8 + (k)] = clock64(); } while (0)
 #define TC_TRACE_DECL_MMA                                                     \
   long long* trace = reinterpret_cast<long long*>(status) + 512;              \
   const bool trace_on = blockIdx.x == 0 && base == (int64_t)50 * tile_stride
 #else
 #define TC_TRACE(k) do { } while (0)
+#define TC_FINE(k) do { } while (0)
 #define TC_TRACE_DECL_MMA do { } while (0)
 #endif
 
@@ -339,7 +352,7 @@ __device__ __noinline__ void true_grad_chunk(const ResidualArgs& a, const float*
 __device__ __forceinline__ float unp(const uint32_t* r, int i) { return (i & 1) ? bf_hi(r[i >> 1]) : bf_lo(r[i >> 1]); }
 
 template <int DP, int NS>
-__global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
+__global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
     fence_mbar_init();
   }
   // every operand byte is finite from the start: zero-weight columns multiply whatever the neighbouring band holds
-  for (uint32_t o = tid * 16; o < S::O_BIAS; o += kThreads * 16) *reinterpret_cast<uint4*>(sm + o) = make_uint4(0, 0, 0, 0);
+  for (uint32_t o = tid * 16; o < S::O_BIAS; o += kLaunchThreads * 16) *reinterpret_cast<uint4*>(sm + o) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
     const float* W0 = a.params + sh.w_off(0);
@@ -381,31 +394,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       *reinterpret_cast<__nv_bfloat16*>(sm + o_hi + off) = hi;
       *reinterpret_cast<__nv_bfloat16*>(sm + o_lo + off) = lo;
     };
-    for (int idx = tid; idx < 32 * S::KX; idx += kThreads) {  // T0X[r = out][c] = W0[c mod DP][r]  ([W0; W0])
+    for (int idx = tid; idx < 32 * S::KX; idx += kLaunchThreads) {  // T0X[r = out][c] = W0[c mod DP][r]  ([W0; W0])
       const int r = idx / S::KX, c = idx % S::KX, ci = c % DP;
       put(S::O_T0XH, S::O_T0XL, S::RG_T0X, r, c, ci < d ? W0[ci * H + r] : 0.f);
     }
-    for (int idx = tid; idx < 32 * S::KV; idx += kThreads) {  // T0V[r = out][c = in] = W0[c][r], columns >= d zero
+    for (int idx = tid; idx < 32 * S::KV; idx += kLaunchThreads) {  // T0V[r = out][c = in] = W0[c][r], columns >= d zero
       const int r = idx / S::KV, c = idx % S::KV;
       put(S::O_T0VH, S::O_T0VL, S::RG_T0V, r, c, c < d ? W0[c * H + r] : 0.f);
     }
-    for (int idx = tid; idx < 32 * 32; idx += kThreads) {
+    for (int idx = tid; idx < 32 * 32; idx += kLaunchThreads) {
       const int r = idx / 32, c = idx % 32;
       put(S::O_T1H, S::O_T1L, S::RG_T1, r, c, W1[c * H + r]);
     }
-    for (int idx = tid; idx < OP * 32; idx += kThreads) {  // T2[r = out (48)][c = in] = W2[c][r], rows >= 40 zero
+    for (int idx = tid; idx < OP * 32; idx += kLaunchThreads) {  // T2[r = out (48)][c = in] = W2[c][r], rows >= 40 zero
       const int r = idx / 32, c = idx % 32;
       put(S::O_T2H, S::O_T2L, S::RG_T2, r, c, r < kOut ? W2[c * kOut + r] : 0.f);
     }
-    for (int j = tid; j < 32; j += kThreads) {
+    for (int j = tid; j < 32; j += kLaunchThreads) {
       bias_s[j] = a.params[sh.b_off(0) + j];
       bias_s[32 + j] = a.params[sh.b_off(1) + j];
     }
-    for (int j = tid; j < OP; j += kThreads) bias_s[64 + j] = j < kOut ? a.params[sh.b_off(2) + j] : 0.f;
+    for (int j = tid; j < OP; j += kLaunchThreads) bias_s[64 + j] = j < kOut ? a.params[sh.b_off(2) + j] : 0.f;
     int ntg = 0;
     if (a.tg.kind == PDEIP_DRIFT_LINEAR) ntg = d * d;
     else if (a.tg.kind == PDEIP_DRIFT_GMM) ntg = a.tg.n_gaussian * d;
-    for (int i = tid; i < ntg; i += kThreads) tp[i] = a.tg.params[i];
+    for (int i = tid; i < ntg; i += kLaunchThreads) tp[i] = a.tg.params[i];
   }
   fence_async_smem();
   fence_before_sync();
@@ -418,6 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
   // ==========================================================================================================
   // MMA warp: one lane issues every tcgen05.mma, phase by phase, slot by slot
   // ==========================================================================================================
+  if (warp >= kEpiThreads / 32) {
+    if constexpr (NS == 1 || kRegsEpi2 > 168) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+  }
   if (is_mma_warp) {
     // weights: K-major views (LBO = 128: next 8 columns, SBO = row-group bytes) and transposed views
     const Desc T0XHK = mk_desc(smem_u32(sm + S::O_T0XH), 128, S::RG_T0X), T0XLK = mk_desc(smem_u32(sm + S::O_T0XL), 128, S::RG_T0X);
@@ -456,11 +472,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
                 commit(mb);
               } break;
               case 1: {  // z1, z1_1, z2^_1
-                mm_fwd<32, 32, 3>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
+                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
               case 2: {  // u, u1, u2^
-                mm_fwd<32, OP, 3>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
+                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
               case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
@@ -542,7 +558,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
       }
       dw_started = 1u;
     }
-  } else {
+  } else if (warp < kEpiThreads / 32) {
+    if constexpr (NS == 2) {
+      if constexpr (kRegsEpi2 > 168) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi2));
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    }
     // ========================================================================================================
     // epilogue warps
     // ========================================================================================================
@@ -747,6 +768,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
           load_chunk(At, (AC_A1 + 2 * half + c) * 128, a1 + 8 * c);
         }
         tm_wait_ld();
+        TC_FINE(0);
         float za[16], zb[16], pz[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -761,7 +783,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
           put_chunk(Z, ((l2 ? ZC_ZA1 : ZC_ZA0) + 2 * half + c) * 128, za + 8 * c);
           put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
         }
+        TC_FINE(1);
         tm_park<16>(LA + (l2 ? C_PZ2 : C_PZ1) + 8 * half, pz);
+        TC_FINE(2);
         TC_PROBE(l2 ? 9 : 12, u16, za, 16);
         TC_PROBE(l2 ? 10 : 13, u16, zb, 16);
         TC_PROBE(l2 ? 11 : 14, u16, pz, 16);
@@ -876,7 +900,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_residual_tc_kernel(const Resi
         TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
       }
       TC_TRACE(7);
+#ifdef PDEIP_TC_TRACE
+      fence_async_smem();
+      TC_FINE(3);
+      fence_before_sync();
+      TC_FINE(4);
+      asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(kThreads) : "memory");
+#else
       epi_arrive(s);
+#endif
       TC_TRACE(2);
     };
 #define PDEIP_TC_PHASE(PH)                       \
@@ -990,7 +1022,7 @@ static int launch_tc(const ResidualArgs& a, int* status, cudaStream_t st) {
   PDEIP_REQUIRE(true_grad_floats(a.tg, a.d) * sizeof(float) <= S::TP_BYTES, PDEIP_ERR_UNSUPPORTED,
                 "tensor path: true-gradient parameters exceed %u bytes", (unsigned)S::TP_BYTES);
   PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-  kern<<<residual_grid(), tc::kThreads, S::TOTAL, st>>>(a, status);
+  kern<<<residual_grid(), tc::kLaunchThreads, S::TOTAL, st>>>(a, status);
   PDEIP_LAUNCH_OK();
   return PDEIP_OK;
 }
@@ -1029,7 +1061,7 @@ extern "C" int pdeip_tensor_path_status(void* stream, int* out_status) {
 extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
   int* status = pdeip::tensor_status_word();
   if (!status) return PDEIP_ERR_CUDA;
-  if (n > 24 * 8 + 48) return PDEIP_ERR_INVALID_ARG;
+  if (n > 24 * 8 + 48 + 16) return PDEIP_ERR_INVALID_ARG;
   if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
   if (cudaMemcpy(out, reinterpret_cast<long long*>(status) + 512, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost) !=
       cudaSuccess)
