@@ -91,12 +91,26 @@ constexpr int kEpiThreads = 256;            // 8 epilogue warps: thread = (point
 constexpr int kThreads = kEpiThreads + 32;  // + one MMA-issuing warp (threads taking part in the named barriers)
 // Launched with a full third warpgroup (three idle warps) so that `setmaxnreg` can move registers: the register file
 // is 16 K per scheduler and each scheduler hosts two epilogue warps and one warp of the third group; the kernel is
-// compiled for 168 registers, the third group shrinks to 24 and the epilogue groups grow to 232 (no spills).
+// compiled for 168 registers, the third group shrinks and the epilogue groups grow (Regs<NS> below; no spills).
 constexpr int kLaunchThreads = 384;
-#ifndef PDEIP_TC_REGS2
-#define PDEIP_TC_REGS2 168  // measured: growing the two-slot kernel past 168 registers is slower (1.95e9 vs 2.38e9 evals/s)
+// (epilogue, third group) register budgets after setmaxnreg (the kernel is compiled and launched at 168)
+#ifndef PDEIP_TC_REGS1_EPI
+#define PDEIP_TC_REGS1_EPI 232
+#define PDEIP_TC_REGS1_MMA 24
 #endif
-constexpr int kRegsEpi = 232, kRegsEpi2 = PDEIP_TC_REGS2, kRegsMma = 24;  // kRegsEpi2: two-slot kernel
+#ifndef PDEIP_TC_REGS2_EPI
+#define PDEIP_TC_REGS2_EPI 208
+#define PDEIP_TC_REGS2_MMA 88
+#endif
+template <int NS>
+struct Regs {
+  static constexpr int kEpi = NS == 2 ? PDEIP_TC_REGS2_EPI : PDEIP_TC_REGS1_EPI;
+  static constexpr int kMma = NS == 2 ? PDEIP_TC_REGS2_MMA : PDEIP_TC_REGS1_MMA;
+  // measured: only the registers released by the third group's warp are available to the two epilogue warps of a
+  // scheduler (2 x 216 + 80 = 512 never returns; 2 x 208 + 88 works)
+  static_assert(2 * (kEpi - 168) <= 168 - kMma && kEpi % 8 == 0 && kMma % 8 == 0 && kMma >= 24 && kEpi <= 256,
+                "setmaxnreg budgets: an impossible request never returns (the kernel hangs)");
+};
 
 template <int V>
 struct IC {
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   // MMA warp: one lane issues every tcgen05.mma, phase by phase, slot by slot
   // ==========================================================================================================
   if (warp >= kEpiThreads / 32) {
-    if constexpr (NS == 1 || kRegsEpi2 > 168) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs<NS>::kMma));
   }
   if (is_mma_warp) {
     // weights: K-major views (LBO = 128: next 8 columns, SBO = row-group bytes) and transposed views
@@ -559,11 +573,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       dw_started = 1u;
     }
   } else if (warp < kEpiThreads / 32) {
-    if constexpr (NS == 2) {
-      if constexpr (kRegsEpi2 > 168) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi2));
-    } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs<NS>::kEpi));
     // ========================================================================================================
     // epilogue warps
     // ========================================================================================================
