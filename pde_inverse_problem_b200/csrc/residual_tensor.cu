@@ -1014,14 +1014,18 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 
 }  // namespace tc
 
+// one status / debug buffer per device (the "no allocation inside the entry points" rule has this one exception: a
+// few hundred KB allocated once per device on the first tensor-path launch)
 static int* tensor_status_word() {
-  static int* w = nullptr;
-  if (!w) {
+  static int* w[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!w[dev]) {
     const size_t bytes = 8192 + 24 * 128 * 48 * sizeof(float);
-    if (cudaMalloc(&w, bytes) != cudaSuccess) return nullptr;
-    cudaMemset(w, 0, bytes);
+    if (cudaMalloc(&w[dev], bytes) != cudaSuccess) return nullptr;
+    cudaMemset(w[dev], 0, bytes);
   }
-  return w;
+  return w[dev];
 }
 
 #ifdef PDEIP_HAVE_TENSOR_PATH

@@ -112,3 +112,24 @@ def test_true_gradient_stored_in_points(cuda, path_name):
         assert relmax(s_x[L.SUM_GT], s_a[L.SUM_GT]) < 1e-5
         assert relmax(s_x[L.SUM_GTRUE2], s_a[L.SUM_GTRUE2]) < 1e-5
         assert relmax(g_x, g_a) < 1e-5
+
+
+@pytest.mark.parametrize("n", [0, 1, 127, 128, 129, 255, 257])
+def test_tensor_path_edge_sizes(cuda, n):
+    """Empty, single-point, and tile-boundary point counts (one or two 128-point slots partially filled): the tensor path
+    agrees with the fp32 path; n = 0 is a no-op that leaves the accumulator at zero."""
+    ops, L = _ops()
+    d = 8
+    p = _params(d)
+    flat = o_model.flatten_params(p).float().to(cuda)
+    g = torch.Generator().manual_seed(70 + n)
+    pts = torch.randn(n, 2 * d, generator=g).to(cuda)
+    spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
+    tg = ops.TrueGrad(L.DRIFT_NONE)
+    s32, g32 = _run(ops, L, cuda, spec, flat, pts, max(n, 1), 0.5, tg, L.PATH_FP32)
+    stc, gtc = _run(ops, L, cuda, spec, flat, pts, max(n, 1), 0.5, tg, L.PATH_TENSOR)
+    if n == 0:
+        assert float(stc.abs().sum()) == 0.0 and float(gtc.abs().sum()) == 0.0
+        return
+    assert relmax(stc[L.SUM_LOSS], s32[L.SUM_LOSS]) < TOL
+    assert relmax(gtc, g32) < 2 * TOL
