@@ -216,7 +216,10 @@ __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const ui
 template <int N>
 __device__ __forceinline__ void mm_outer(uint32_t d, Desc a_m, uint32_t a_off, uint32_t a_rg, Desc b_m, uint32_t b_off,
                                          uint32_t b_rg, uint32_t accumulate) {
-  constexpr uint32_t idesc = make_idesc(N, 1, 1);
+  // M = 64 instruction shape: only rows 0..31 of a dW block are wanted, and the A fetch (the cost of these MMAs:
+  // both operands come from shared memory) halves.  Row i of D lands in TMEM lane (i % 16) + 32 (i / 16)
+  // (measured: tools/umma_m64_probe.py, tests/test_gpu_umma.py).
+  constexpr uint32_t idesc = (make_idesc(N, 1, 1) & ~(0x1Fu << 24)) | ((uint32_t)(64 >> 4) << 24);
 #pragma unroll
   for (int k = 0; k < 128; k += 16)
     mma(d, a_m, a_off + (k >> 3) * a_rg, b_m, b_off + (k >> 3) * b_rg, idesc, k > 0 ? 1u : accumulate);
@@ -946,20 +949,24 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     float* part = a.ws + (int64_t)blockIdx.x * a.pstride;
     float* red = reinterpret_cast<float*>(sm);  // [4 quadrants][128] bias sums + [8 warps][8] loss sums
     const float wt = a.weight;
-    if (ok && q == 0) {  // TMEM lanes 0..31 = input unit of the dW blocks
+    if (ok && q < 2) {  // M = 64 dW blocks: input unit i = 16 q + lane sits in TMEM lane 32 q + lane, lane < 16
+      const uint32_t LQ = TB + ((uint32_t)(q * 32) << 16);
+      const int iu = 16 * q + lane;
       float w2[24], w1[16], w0[16];
-      tm_ldf<24>(TB + C_DW2 + u24, w2);
-      tm_ldf<16>(TB + C_DW1 + u16, w1);
-      tm_ldf<16>(TB + C_DW0 + u16, w0);
+      tm_ldf<24>(LQ + C_DW2 + u24, w2);
+      tm_ldf<16>(LQ + C_DW1 + u16, w1);
+      tm_ldf<16>(LQ + C_DW0 + u16, w0);
       tm_wait_ld();
+      if (lane < 16) {
 #pragma unroll
-      for (int i = 0; i < 24; ++i)
-        if (u24 + i < kOut) part[sh.w_off(2) + lane * kOut + u24 + i] += wt * w2[i];
+        for (int i = 0; i < 24; ++i)
+          if (u24 + i < kOut) part[sh.w_off(2) + iu * kOut + u24 + i] += wt * w2[i];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) part[sh.w_off(1) + lane * H + u16 + i] += wt * w1[i];
-      if (lane < d) {
+        for (int i = 0; i < 16; ++i) part[sh.w_off(1) + iu * H + u16 + i] += wt * w1[i];
+        if (iu < d) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) part[sh.w_off(0) + lane * H + u16 + i] += wt * w0[i];
+          for (int i = 0; i < 16; ++i) part[sh.w_off(0) + iu * H + u16 + i] += wt * w0[i];
+        }
       }
     }
     // bias gradients: sum over the 32 rows of the warp, then over the 4 quadrants through shared memory

@@ -9,6 +9,7 @@ namespace pdeip {
 // mode 1: D[m][n] = sum_k A[m][k] * B[k][n]      A [128][K], B [K][N]        (B transposed view)
 // mode 2: D[m][n] = sum_r A[r][m] * B[r][n]      A [K][128], B [K][N]        (both transposed views)
 // mode 3: TMEM st/ld round trip: D[m][n] = A[m][n] (K = N)
+// mode 4: as mode 2 with the M = 64 instruction shape; TMEM is pre-filled with -777 so the dump shows which lanes are written
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ B, float* __restrict__ D,
                                                             int K, int N, int* __restrict__ status) {
@@ -16,7 +17,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int a_rows = (mode == 2) ? K : 128, a_cols = (mode == 2) ? 128 : K;
+  const int a_rows = (mode == 2 || mode == 4) ? K : 128, a_cols = (mode == 2 || mode == 4) ? 128 : K;
   const int b_rows = (mode == 0) ? N : K, b_cols = (mode == 0) ? K : N;
   const uint32_t a_rg = (uint32_t)(a_cols / 8) * 128u, b_rg = (uint32_t)(b_cols / 8) * 128u;
   uint8_t* a_tile = sm;
@@ -50,6 +51,14 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   const uint32_t tbase = tmem_base_s;
   const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
   bool ok = true;
+  if (mode == 4) {  // sentinel fill (every warp its own lane quadrant), ordered before the MMA by the barrier below
+    float v[8];
+    for (int i = 0; i < 8; ++i) v[i] = -777.f;
+    for (int c = 0; c < N; c += 8) umma::tmem_st8(lane_addr + c, v);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   if (mode == 3) {
     for (int c = 0; c < N; c += 8) {
       float v[8];
@@ -61,7 +70,15 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
       const uint32_t at = umma::smem_u32(a_tile), bt = umma::smem_u32(b_tile);
       if (mode == 0) umma::gemm_kk(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
       else if (mode == 1) umma::gemm_km(tbase, at, a_rg, 0, bt, b_rg, 0, 0, K, N, 0);
-      else umma::gemm_mm(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
+      else if (mode == 2) umma::gemm_mm(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
+      else {
+        const uint32_t idesc = (umma::make_idesc(N, 1, 1) & ~(0x1Fu << 24)) | ((uint32_t)(64 >> 4) << 24);  // M = 64
+        for (int k = 0; k < K; k += 16) {
+          const uint64_t ad = umma::make_desc(at + (uint32_t)(k >> 3) * a_rg, a_rg, 128u);
+          const uint64_t bd = umma::make_desc(bt + (uint32_t)(k >> 3) * b_rg, b_rg, 128u);
+          umma::mma_bf16(tbase, ad, bd, idesc, (k > 0) ? 1u : 0u);
+        }
+      }
       umma::commit(umma::smem_u32(&mbar));
     }
     ok = umma::mbar_wait(umma::smem_u32(&mbar), 0);
@@ -87,7 +104,7 @@ using namespace pdeip;
 
 extern "C" int pdeip_debug_umma(int mode, const float* A, const float* B, float* D, int K, int N, int* status,
                                 void* stream) {
-  PDEIP_REQUIRE(mode >= 0 && mode <= 3 && A && D && status, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  PDEIP_REQUIRE(mode >= 0 && mode <= 4 && A && D && status, PDEIP_ERR_INVALID_ARG, "bad arguments");
   PDEIP_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 64, PDEIP_ERR_INVALID_ARG,
                 "K must be a multiple of 16 in [16,128], N a multiple of 16 in [16,64]");
   const size_t smem = (size_t)128 * 128 * 2 + (size_t)128 * 64 * 2 + 1024;

@@ -38,3 +38,20 @@ def test_tmem_store_load_roundtrip(cuda):
     A = torch.randn(128, 32, device=cuda)
     D = _run(3, A, None, 32, 32, cuda)
     assert torch.equal(D, A)
+
+
+def test_m64_instruction_shape_lane_mapping(cuda):
+    """tcgen05.mma with M = 64 (cta_group::1): row i of D is written to TMEM lane (i % 16) + 32 (i / 16); the other
+    lanes keep their contents.  The residual kernel's dW GEMMs rely on this mapping."""
+    K, N = 32, 32
+    g = torch.Generator().manual_seed(64)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    A2 = bf(torch.randn(K, 128, generator=g)).to(cuda)
+    B1 = bf(torch.randn(K, N, generator=g)).to(cuda)
+    D = _run(4, A2, B1, K, N, cuda)
+    ref = A2.T @ B1
+    for i in range(64):
+        lane = (i % 16) + 32 * (i // 16)
+        assert torch.allclose(D[lane], ref[i], rtol=1e-4, atol=1e-4), i
+    untouched = [l for l in range(128) if (l % 32) >= 16]
+    assert torch.all(D[untouched] == -777.0)
