@@ -653,26 +653,24 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       long long* trace = reinterpret_cast<long long*>(status) + 512;
       const bool trace_on = blockIdx.x == 0 && tid == 0 && base == (int64_t)50 * tile_stride;
 #endif
-      TC_TRACE(0);
-#ifdef PDEIP_TC_TRACE
-      if (trace_on && !(ph == 0 && first)) {  // latency and outcome of the first poll
-        const long long ta = clock64();
-        const bool hit = mbar_try_wait(smem_u32(mbar_p + s), (par >> s) & 1u);
-        const long long tb = clock64();
-        trace[192 + (ph * 2 + s) * 2] = tb - ta;
-        trace[192 + (ph * 2 + s) * 2 + 1] = hit ? 1 : 0;
-      }
-#endif
-      if (!(ph == 0 && first)) {  // GEMMs of the previous phase of this slot (P11 of the previous tile before E0)
-        if (ok && !mbar_wait(smem_u32(mbar_p + s), (par >> s) & 1u)) {
-          ok = false;
-          atomicExch(status, 1);
+      // wait for the GEMMs of the previous phase of this slot (P11 of the previous tile before E0).  Phases that also
+      // read operands which do not come from those GEMMs (own bf16 chunks in shared memory, parked TMEM values) issue
+      // and unpack them BEFORE this wait, so that the hand-off latency is spent on useful work.
+      auto wait_gemm = [&]() {
+        TC_TRACE(0);
+        if (!(ph == 0 && first)) {
+          if (ok && !mbar_wait(smem_u32(mbar_p + s), (par >> s) & 1u)) {
+            ok = false;
+            atomicExch(status, 1);
+          }
+          par ^= 1u << s;
+          TC_TRACE(3);
+          fence_after_sync();
         }
-        par ^= 1u << s;
-        TC_TRACE(3);
-        fence_after_sync();
-      }
-      TC_TRACE(1);
+        TC_TRACE(1);
+      };
+      constexpr bool kEarlyLoads = DP <= 16;  // at d = 32 the values held across the wait cost more in spills than they hide
+      if constexpr (ph <= 3 || ph == 6 || !kEarlyLoads) wait_gemm();
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
         auto emit = [&](const float (&xin)[NI][8]) {
 #pragma unroll
@@ -774,14 +772,16 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const uint8_t* At = l2 ? A2 : A1;
         float aa[16], ab1[16], t[16], a1[16];
         uint32_t s1p[8];
-        tm_ldf<16>(LA + (l2 ? C_AA2 : C_AA1) + u16, aa);
-        tm_ldf<16>(LA + (l2 ? C_AB12 : C_AB11) + u16, ab1);
         tm_ldp<16>(LA + (l2 ? C_S1P2 : C_S1P1) + 8 * half, s1p);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           load_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
           load_chunk(At, (AC_A1 + 2 * half + c) * 128, a1 + 8 * c);
         }
+        tm_wait_ld();
+        if constexpr (kEarlyLoads) wait_gemm();
+        tm_ldf<16>(LA + (l2 ? C_AA2 : C_AA1) + u16, aa);
+        tm_ldf<16>(LA + (l2 ? C_AB12 : C_AB11) + u16, ab1);
         tm_wait_ld();
         TC_FINE(0);
         float za[16], zb[16], pz[16];
@@ -850,10 +850,12 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         uint8_t* const At = l1 ? A1 : A2;
         float zg[16], a2[16];
         uint32_t s1p[8];
-        tm_ldf<16>(LA + (l1 ? C_ZG0 : C_ZG1) + u16, zg);
         tm_ldp<16>(LA + (l1 ? C_S1P1 : C_S1P2) + 8 * half, s1p);
 #pragma unroll
         for (int c = 0; c < 2; ++c) load_chunk(At, (AC_C + 2 * half + c) * 128, a2 + 8 * c);
+        tm_wait_ld();
+        if constexpr (kEarlyLoads) wait_gemm();
+        tm_ldf<16>(LA + (l1 ? C_ZG0 : C_ZG1) + u16, zg);
         tm_wait_ld();
         float ag[16], cc[16];
 #pragma unroll
@@ -871,8 +873,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // E9: s0 = s0p + 8 ug^;  db2 += s0
         float ug[24], s0[24];
         uint32_t spp[12];
-        tm_ldf<24>(LA + C_UG + u24, ug);
         tm_ldp<24>(LA + C_S0P + 12 * half, spp);
+        tm_wait_ld();
+        if constexpr (kEarlyLoads) wait_gemm();
+        tm_ldf<24>(LA + C_UG + u24, ug);
         tm_wait_ld();
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
@@ -892,8 +896,6 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const uint8_t* At = l2 ? A2 : A1;
         float ab[16], aa[16], t[16], cc[16];
         uint32_t s1p[8], pzp[8];
-        tm_ldf<16>(LA + (l2 ? C_AB2 : C_AB1) + u16, ab);
-        tm_ldf<16>(LA + (l2 ? C_AA2R : C_AA1R) + u16, aa);
         tm_ldp<16>(LA + (l2 ? C_S1P2 : C_S1P1) + 8 * half, s1p);
         tm_ldp<16>(LA + (l2 ? C_PZ2 : C_PZ1) + 8 * half, pzp);
 #pragma unroll
@@ -901,6 +903,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           load_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
           load_chunk(At, (AC_C + 2 * half + c) * 128, cc + 8 * c);
         }
+        tm_wait_ld();
+        if constexpr (kEarlyLoads) wait_gemm();
+        tm_ldf<16>(LA + (l2 ? C_AB2 : C_AB1) + u16, ab);
+        tm_ldf<16>(LA + (l2 ? C_AA2R : C_AA1R) + u16, aa);
         tm_wait_ld();
         float zb[16];
 #pragma unroll
