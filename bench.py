@@ -371,9 +371,8 @@ def run_reference(args):
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would be a second line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: NCCL's debug output (the version banner at NCCL_DEBUG >= VERSION) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
