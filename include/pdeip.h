@@ -110,6 +110,19 @@ int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
                        int schedule, int state_layout, int traj_layout,
                        int emit_every, int emit_offset, int emit_drift, void* stream);
 
+/* Same call with a kernel path.  PDEIP_PATH_FP32: CUDA-core fp32 arithmetic throughout (rtol 1e-5 class).
+ * PDEIP_PATH_TENSOR: in the production configuration (Philox noise, REFERENCE schedule, AOS state, TIME_SOA
+ * trajectory with emit_drift, emit_every 1) with the GMM drift, d = 16 or 32 and n_gaussian <= 64, the particle x
+ * centre contraction and the softmax-weighted centre sum run on tcgen05 with bf16 hi + lo split operands
+ * ("bf16 GEMM path", rtol 1e-2 class; measured ~1e-4); every other configuration runs the fp32 kernels. */
+int pdeip_kl_integrate_path(const float* z0, float* z_last, float* traj, float* tau,
+                            int64_t n_particles, int d, int n_steps, float dt, float gamma,
+                            int drift_kind, const float* drift_params, int n_gaussian, float sigma,
+                            const float* noise, const float* tau0,
+                            uint64_t seed, uint64_t particle_offset, uint32_t step_offset,
+                            int schedule, int state_layout, int traj_layout,
+                            int emit_every, int emit_offset, int emit_drift, int path, void* stream);
+
 /* the normals / uniforms pdeip_kl_integrate draws in Philox mode (for parity tests):
  * normals [N][n_draws][d] for steps step_offset..step_offset+n_draws-1; uniforms [N] (tau0/dt). */
 int pdeip_philox_normals(float* out, int64_t n_particles, int n_draws, int d, uint64_t seed,

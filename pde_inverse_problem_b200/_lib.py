@@ -47,6 +47,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_sm_count": (_i, []),
     "pdeip_kl_integrate": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _f, _i, _p, _i, _f, _p, _p, _u64, _u64, _u32,
                                 _i, _i, _i, _i, _i, _i, _p]),
+    "pdeip_kl_integrate_path": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _f, _i, _p, _i, _f, _p, _p, _u64, _u64, _u32,
+                                     _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdeip_philox_normals": (_i, [_p, _l, _i, _i, _u64, _u64, _u32, _p]),
     "pdeip_philox_uniforms": (_i, [_p, _l, _u64, _u64, _p]),
     "pdeip_philox_raw": (_i, [_p, _p, _p, _l, _p]),

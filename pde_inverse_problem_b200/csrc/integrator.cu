@@ -7,38 +7,13 @@
 // trajectory samples and the final state — 2d*4 bytes per emitted particle-step.
 #include "common.cuh"
 #include "drift.cuh"
+#include "integrator_args.cuh"
 #include "philox.cuh"
 
 #include <stdlib.h>
 
 namespace pdeip {
 
-struct IntegrateArgs {
-  const float* z0;
-  float* z_last;
-  float* traj;
-  float* tau;
-  int64_t n;
-  int d;
-  int n_steps;
-  float dt;
-  float gamma;
-  const float* drift_params;
-  int n_gaussian;
-  float inv_sigma2;
-  const float* noise;
-  const float* tau0;
-  uint64_t seed;
-  uint64_t particle_offset;
-  uint32_t step_offset;
-  int schedule;
-  int state_layout;
-  int traj_layout;
-  int emit_every;
-  int emit_offset;
-  int s_emit;  // number of emitted samples
-  int emit_drift;  // 1: every emitted sample carries grad U(x) as components [2d, 3d)
-};
 
 template <int DP>
 __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
@@ -427,8 +402,12 @@ static int launch_integrate_fast(const IntegrateArgs& a, int drift_kind, cudaStr
 }
 
 template <int DP>
-static int launch_integrate(const IntegrateArgs& a, int drift_kind, cudaStream_t st) {
-  if (fast_path_ok(a, drift_kind, DP)) return launch_integrate_fast<DP>(a, drift_kind, st);
+static int launch_integrate(const IntegrateArgs& a, int drift_kind, int path, cudaStream_t st) {
+  if (fast_path_ok(a, drift_kind, DP)) {
+    // PDEIP_PATH_TENSOR: the GMM distance contraction on tcgen05 where that kernel exists, else the fp32 kernel
+    if (path == PDEIP_PATH_TENSOR && integrate_tensor_ok(a, drift_kind)) return launch_integrate_tensor(a, st);
+    return launch_integrate_fast<DP>(a, drift_kind, st);
+  }
   const int block = 128;
   const int64_t grid = (a.n + block - 1) / block;
   size_t smem = 0;
@@ -513,13 +492,14 @@ __global__ void gaussian_sample_kernel(float* out, int64_t n, int dim, const flo
 
 using namespace pdeip;
 
-extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
-                                  int64_t n_particles, int d, int n_steps, float dt, float gamma,
-                                  int drift_kind, const float* drift_params, int n_gaussian, float sigma,
-                                  const float* noise, const float* tau0, uint64_t seed,
-                                  uint64_t particle_offset, uint32_t step_offset, int schedule,
-                                  int state_layout, int traj_layout, int emit_every, int emit_offset,
-                                  int emit_drift, void* stream) {
+extern "C" int pdeip_kl_integrate_path(const float* z0, float* z_last, float* traj, float* tau,
+                                       int64_t n_particles, int d, int n_steps, float dt, float gamma,
+                                       int drift_kind, const float* drift_params, int n_gaussian, float sigma,
+                                       const float* noise, const float* tau0, uint64_t seed,
+                                       uint64_t particle_offset, uint32_t step_offset, int schedule,
+                                       int state_layout, int traj_layout, int emit_every, int emit_offset,
+                                       int emit_drift, int path, void* stream) {
+  PDEIP_REQUIRE(path == PDEIP_PATH_FP32 || path == PDEIP_PATH_TENSOR, PDEIP_ERR_INVALID_ARG, "unknown path %d", path);
   PDEIP_REQUIRE(z0 != nullptr, PDEIP_ERR_INVALID_ARG, "z0 is NULL");
   PDEIP_REQUIRE(n_particles >= 0 && d >= 1 && d <= 32, PDEIP_ERR_UNSUPPORTED,
                 "integrator supports 1 <= d <= 32 (got d=%d)", d);
@@ -548,11 +528,23 @@ extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, f
   const int n_samples = n_steps;  // both schedules expose n_steps samples
   a.s_emit = (n_samples - emit_offset + emit_every - 1) / emit_every;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d <= 2) return launch_integrate<2>(a, drift_kind, st);
-  if (d <= 4) return launch_integrate<4>(a, drift_kind, st);
-  if (d <= 8) return launch_integrate<8>(a, drift_kind, st);
-  if (d <= 16) return launch_integrate<16>(a, drift_kind, st);
-  return launch_integrate<32>(a, drift_kind, st);
+  if (d <= 2) return launch_integrate<2>(a, drift_kind, path, st);
+  if (d <= 4) return launch_integrate<4>(a, drift_kind, path, st);
+  if (d <= 8) return launch_integrate<8>(a, drift_kind, path, st);
+  if (d <= 16) return launch_integrate<16>(a, drift_kind, path, st);
+  return launch_integrate<32>(a, drift_kind, path, st);
+}
+
+extern "C" int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
+                                  int64_t n_particles, int d, int n_steps, float dt, float gamma,
+                                  int drift_kind, const float* drift_params, int n_gaussian, float sigma,
+                                  const float* noise, const float* tau0, uint64_t seed,
+                                  uint64_t particle_offset, uint32_t step_offset, int schedule,
+                                  int state_layout, int traj_layout, int emit_every, int emit_offset,
+                                  int emit_drift, void* stream) {
+  return pdeip_kl_integrate_path(z0, z_last, traj, tau, n_particles, d, n_steps, dt, gamma, drift_kind, drift_params,
+                                 n_gaussian, sigma, noise, tau0, seed, particle_offset, step_offset, schedule,
+                                 state_layout, traj_layout, emit_every, emit_offset, emit_drift, PDEIP_PATH_FP32, stream);
 }
 
 extern "C" int pdeip_philox_normals(float* out, int64_t n_particles, int n_draws, int d, uint64_t seed,

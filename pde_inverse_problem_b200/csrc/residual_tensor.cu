@@ -1031,7 +1031,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 
 // one status / debug buffer per device (the "no allocation inside the entry points" rule has this one exception: a
 // few hundred KB allocated once per device on the first tensor-path launch)
-static int* tensor_status_word() {
+int* tensor_status_word() {
   static int* w[64] = {nullptr};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;

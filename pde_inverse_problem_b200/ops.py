@@ -48,10 +48,11 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
                  state_layout: int = L.LAYOUT_AOS, traj_layout: int = L.TRAJ_PARTICLE_MAJOR,
                  want_traj: bool = True, want_tau: bool = False, emit_every: int = 1, emit_offset: int = 0,
                  traj_out: Optional[torch.Tensor] = None, z_last_out: Optional[torch.Tensor] = None,
-                 emit_drift: bool = False,
+                 emit_drift: bool = False, path: int = L.PATH_FP32,
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """pdeip_kl_integrate.  z0: [N,2d] (AOS) or [2d,N] (SOA).  Returns (z_last, traj|None, tau|None).
-    emit_drift: every trajectory sample is [x, v, grad U(x)] (3d components)."""
+    emit_drift: every trajectory sample is [x, v, grad U(x)] (3d components).
+    path: PATH_TENSOR runs the GMM drift contraction on tcgen05 where that kernel exists (see pdeip.h)."""
     lib = L.load()
     z0 = _f32(z0, "z0")
     if state_layout == L.LAYOUT_AOS:
@@ -81,11 +82,12 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
         else:
             traj = torch.empty(shape, device=z0.device, dtype=torch.float32)
     tau = torch.empty((n, n_steps), device=z0.device, dtype=torch.float32) if want_tau else None
-    st = lib.pdeip_kl_integrate(_ptr(z0), _ptr(z_last), _ptr(traj), _ptr(tau), n, d, n_steps, dt, gamma,
-                                drift_kind, _ptr(drift_params), n_gaussian, sigma, _ptr(noise), _ptr(tau0),
-                                seed & 0xFFFFFFFFFFFFFFFF, particle_offset, step_offset, schedule, state_layout,
-                                traj_layout, emit_every, emit_offset, 1 if emit_drift else 0, _stream())
-    L.check(st, "pdeip_kl_integrate")
+    st = lib.pdeip_kl_integrate_path(_ptr(z0), _ptr(z_last), _ptr(traj), _ptr(tau), n, d, n_steps, dt, gamma,
+                                     drift_kind, _ptr(drift_params), n_gaussian, sigma, _ptr(noise), _ptr(tau0),
+                                     seed & 0xFFFFFFFFFFFFFFFF, particle_offset, step_offset, schedule,
+                                     state_layout, traj_layout, emit_every, emit_offset, 1 if emit_drift else 0,
+                                     path, _stream())
+    L.check(st, "pdeip_kl_integrate_path")
     launch_counter["n"] += 1
     return z_last, traj, tau
 
