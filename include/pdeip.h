@@ -15,6 +15,7 @@
  *     in methods/consistency_instances/kinetic_fokker_planck.py:13-15;
  *   - `layout` arguments: PDEIP_LAYOUT_AOS  rows of `dim` floats, point-major        [n][dim]
  *                         PDEIP_LAYOUT_SOA  component planes                         [dim][n]
+ *                         PDEIP_LAYOUT_BLOCK128  128-point blocks of component planes  [n/128][dim][128]
  *   - MLP parameters are one flat buffer [W0 (d x H, row-major [in][out]), b0 (H), W1 (H x H), b1,
  *     ..., W_last (H x 40), b_last (40)] — Flax's layers_i/{kernel,bias} order (core/model.py:42-43);
  *   - sums, not means: residual kernels return weighted SUMS over the points they were given
@@ -40,11 +41,14 @@ extern "C" {
 
 #define PDEIP_LAYOUT_AOS 0
 #define PDEIP_LAYOUT_SOA 2
+#define PDEIP_LAYOUT_BLOCK128 3 /* [n/128][dim][128]: blocks of 128 points, component planes inside a block (n % 128 == 0) */
 
 /* trajectory layouts of pdeip_kl_integrate */
 #define PDEIP_TRAJ_PARTICLE_MAJOR 0 /* [N][S_emit][2d]  (reference: utils/sampling_utils.py:52 under vmap) */
 #define PDEIP_TRAJ_TIME_MAJOR     1 /* [S_emit][N][2d] */
 #define PDEIP_TRAJ_TIME_SOA       2 /* [2d][S_emit][N]: an SOA point set of S_emit*N points, point = s*N + n */
+#define PDEIP_TRAJ_BLOCK128       3 /* [S_emit][N/128][2d][128] (N % 128 == 0): a PDEIP_LAYOUT_BLOCK128 point set of
+                                     S_emit*N points, point = s*N + n; all stores of a step are base + constant */
 
 /* drift kinds */
 #define PDEIP_DRIFT_NONE      0 /* VoidPotential, core/potential.py:27-29 */

@@ -22,8 +22,8 @@ class PdeipError(RuntimeError):
 
 # constants of include/pdeip.h
 OK = 0
-LAYOUT_AOS, LAYOUT_SOA = 0, 2
-TRAJ_PARTICLE_MAJOR, TRAJ_TIME_MAJOR, TRAJ_TIME_SOA = 0, 1, 2
+LAYOUT_AOS, LAYOUT_SOA, LAYOUT_BLOCK128 = 0, 2, 3
+TRAJ_PARTICLE_MAJOR, TRAJ_TIME_MAJOR, TRAJ_TIME_SOA, TRAJ_BLOCK128 = 0, 1, 2, 3
 DRIFT_NONE, DRIFT_LINEAR, DRIFT_GMM, DRIFT_MEANFIELD, DRIFT_IN_POINTS = 0, 1, 2, 3, 4
 SCHEDULE_REFERENCE, SCHEDULE_UNIFORM = 0, 1
 MODEL_MLP, MODEL_GMM, MODEL_QUADRATIC = 0, 1, 2

@@ -121,8 +121,10 @@ extern "C" int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes
                 "workspace too small: need %zu bytes, got %zu", residual_ws_bytes(P), workspace_bytes);
   PDEIP_REQUIRE(params != nullptr, PDEIP_ERR_INVALID_ARG, "params is NULL");
   PDEIP_REQUIRE(n_points >= 0, PDEIP_ERR_INVALID_ARG, "n_points < 0");
-  PDEIP_REQUIRE(layout == PDEIP_LAYOUT_AOS || layout == PDEIP_LAYOUT_SOA, PDEIP_ERR_INVALID_ARG, "bad layout %d",
-                layout);
+  PDEIP_REQUIRE(layout == PDEIP_LAYOUT_AOS || layout == PDEIP_LAYOUT_SOA || layout == PDEIP_LAYOUT_BLOCK128,
+                PDEIP_ERR_INVALID_ARG, "bad layout %d", layout);
+  PDEIP_REQUIRE(layout != PDEIP_LAYOUT_BLOCK128 || n_points % 128 == 0, PDEIP_ERR_INVALID_ARG,
+                "PDEIP_LAYOUT_BLOCK128 needs n_points %% 128 == 0 (got %lld)", (long long)n_points);
   PDEIP_REQUIRE(true_kind == PDEIP_DRIFT_NONE || true_kind == PDEIP_DRIFT_LINEAR || true_kind == PDEIP_DRIFT_GMM ||
                     true_kind == PDEIP_DRIFT_IN_POINTS,
                 PDEIP_ERR_INVALID_ARG, "true_kind must be NONE, LINEAR, GMM or IN_POINTS");

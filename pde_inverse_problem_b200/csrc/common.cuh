@@ -52,8 +52,9 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// element (point n, component c) of a [n][dim] (AOS) or [dim][n] (SOA) array
+// element (point n, component c) of a [n][dim] (AOS), [dim][n] (SOA) or [n/128][dim][128] (BLOCK128) array
 __device__ __forceinline__ int64_t elem_index(int layout, int64_t n, int c, int64_t n_total, int dim) {
+  if (layout == PDEIP_LAYOUT_BLOCK128) return ((n >> 7) * dim + c) * 128 + (n & 127);
   return layout == PDEIP_LAYOUT_AOS ? n * dim + c : (int64_t)c * n_total + n;
 }
 

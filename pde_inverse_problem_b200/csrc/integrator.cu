@@ -19,6 +19,16 @@ template <int DP>
 __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
                                            int d, int C, int s_e, int s_emit, const float (&q)[DP],
                                            const float (&p)[DP]) {
+  if (layout == PDEIP_TRAJ_BLOCK128) {  // [S_emit][N/128][C][128]
+    float* o = base + (((int64_t)s_e * (n_total >> 7) + (n >> 7)) * C) * 128 + (n & 127);
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) {
+        __stcs(o + i * 128, q[i]);
+        __stcs(o + (d + i) * 128, p[i]);
+      }
+    return;
+  }
   if (layout == PDEIP_TRAJ_TIME_SOA) {  // [2d][S_emit][N]: component planes, each plane time-major
     float* o = base + (int64_t)s_e * n_total + n;
     const int64_t plane = (int64_t)s_emit * n_total;
@@ -53,6 +63,13 @@ __device__ __forceinline__ void emit_state(float* __restrict__ base, int layout,
 template <int DP>
 __device__ __forceinline__ void emit_drift_vals(float* __restrict__ base, int layout, int64_t n, int64_t n_total,
                                                 int d, int C, int s_e, int s_emit, const float (&g)[DP]) {
+  if (layout == PDEIP_TRAJ_BLOCK128) {
+    float* o = base + (((int64_t)s_e * (n_total >> 7) + (n >> 7)) * C) * 128 + (n & 127);
+#pragma unroll
+    for (int i = 0; i < DP; ++i)
+      if (i < d) __stcs(o + (2 * d + i) * 128, g[i]);
+    return;
+  }
   if (layout == PDEIP_TRAJ_TIME_SOA) {
     float* o = base + (int64_t)s_e * n_total + n;
     const int64_t plane = (int64_t)s_emit * n_total;
@@ -285,7 +302,8 @@ __device__ __forceinline__ void linear_grad_fast(const float2 (&x)[DP / 2], cons
 #ifndef PDEIP_FAST_MINB
 #define PDEIP_FAST_MINB 4
 #endif
-template <int DP, int DRIFT>
+// BLK: trajectory in PDEIP_TRAJ_BLOCK128 (every store of a step is base + immediate) instead of PDEIP_TRAJ_TIME_SOA
+template <int DP, int DRIFT, bool BLK>
 __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integrate_fast_kernel(const IntegrateArgs a, int k_pad) {
   static_assert(DP % 4 == 0, "packed path needs d % 4 == 0");
   extern __shared__ __align__(16) float smem[];
@@ -317,8 +335,10 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
   const float t0 = philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
   const float c2 = -0.5f * a.inv_sigma2 * 1.4426950408889634f;
   const int S = a.n_steps;
-  const int64_t plane = (int64_t)S * a.n;  // floats per component plane of the [3d][S][N] trajectory
-  float* o = a.traj + n;                   // sample 0, component 0 of this particle
+  // BLK: element (sample s, block b, component c, lane l) at ((s B + b) 3d + c) 128 + l ; else c S N + s N + n
+  const int64_t plane = BLK ? 128 : (int64_t)S * a.n;                             // floats between components
+  const int64_t sstride = BLK ? (int64_t)gridDim.x * (3 * DP * 128) : a.n;        // floats between samples
+  float* o = BLK ? a.traj + ((int64_t)blockIdx.x * (3 * DP) * 128 + threadIdx.x) : a.traj + n;  // sample 0, comp 0
 #pragma unroll 1
   for (int s = 0; s <= S; ++s) {
     const float h = (s == 0) ? t0 : ((s == S) ? a.dt - t0 : a.dt);  // sampling_utils.py:33,45-46
@@ -326,11 +346,16 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
     if constexpr (DRIFT == PDEIP_DRIFT_GMM) gmm_grad_fast<DP>(q, smem, k_pad, c2, a.inv_sigma2, g);
     else linear_grad_fast<DP>(q, smem, g);
     if (s >= 1) {  // grad U at the state emitted as sample s - 1
-      float* og = o - a.n + 2 * DP * plane;
+      float* og = o - sstride + 2 * DP * plane;
 #pragma unroll
       for (int i = 0; i < DP / 2; ++i) {
-        __stcs(og + (int64_t)(2 * i) * plane, g[i].x);
-        __stcs(og + (int64_t)(2 * i + 1) * plane, g[i].y);
+        if constexpr (BLK) {
+          __stcs(og + (2 * i) * 128, g[i].x);
+          __stcs(og + (2 * i + 1) * 128, g[i].y);
+        } else {
+          __stcs(og + (int64_t)(2 * i) * plane, g[i].x);
+          __stcs(og + (int64_t)(2 * i + 1) * plane, g[i].y);
+        }
       }
     }
     // p' = p - h g + sqrt(2 h) xi - gamma h p ;  q' = q + h p'     (sampling_utils.py:14-20)
@@ -355,12 +380,19 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
     if (s < S) {
 #pragma unroll
       for (int i = 0; i < DP / 2; ++i) {
-        __stcs(o + (int64_t)(2 * i) * plane, q[i].x);
-        __stcs(o + (int64_t)(2 * i + 1) * plane, q[i].y);
-        __stcs(o + (int64_t)(DP + 2 * i) * plane, p[i].x);
-        __stcs(o + (int64_t)(DP + 2 * i + 1) * plane, p[i].y);
+        if constexpr (BLK) {
+          __stcs(o + (2 * i) * 128, q[i].x);
+          __stcs(o + (2 * i + 1) * 128, q[i].y);
+          __stcs(o + (DP + 2 * i) * 128, p[i].x);
+          __stcs(o + (DP + 2 * i + 1) * 128, p[i].y);
+        } else {
+          __stcs(o + (int64_t)(2 * i) * plane, q[i].x);
+          __stcs(o + (int64_t)(2 * i + 1) * plane, q[i].y);
+          __stcs(o + (int64_t)(DP + 2 * i) * plane, p[i].x);
+          __stcs(o + (int64_t)(DP + 2 * i + 1) * plane, p[i].y);
+        }
       }
-      o += a.n;
+      o += sstride;
     }
   }
   {
@@ -378,7 +410,8 @@ static bool fast_path_ok(const IntegrateArgs& a, int drift_kind, int DP) {
   return a.d == DP && DP % 4 == 0 && (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR) && !a.noise &&
          !a.tau0 && !a.tau && a.traj && a.z_last && a.emit_drift && a.emit_every == 1 && a.emit_offset == 0 &&
          a.schedule == PDEIP_SCHEDULE_REFERENCE && a.state_layout == PDEIP_LAYOUT_AOS &&
-         a.traj_layout == PDEIP_TRAJ_TIME_SOA && getenv("PDEIP_NO_FAST_INTEGRATOR") == nullptr;
+         (a.traj_layout == PDEIP_TRAJ_TIME_SOA || a.traj_layout == PDEIP_TRAJ_BLOCK128) &&
+         getenv("PDEIP_NO_FAST_INTEGRATOR") == nullptr;
 }
 
 template <int DP>
@@ -390,9 +423,15 @@ static int launch_integrate_fast(const IntegrateArgs& a, int drift_kind, cudaStr
       const int k_pad = (a.n_gaussian + kGmmTile - 1) / kGmmTile * kGmmTile;
       const size_t smem = sizeof(float) * (size_t)k_pad * DP;
       PDEIP_REQUIRE(smem <= 48 * 1024, PDEIP_ERR_UNSUPPORTED, "GMM centres exceed 48 KB of shared memory");
-      kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
+      if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM, true><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
+      else
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM, false><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
     } else {
-      kl_integrate_fast_kernel<DP, PDEIP_DRIFT_LINEAR><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
+      if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_LINEAR, true><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
+      else
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_LINEAR, false><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
     }
     PDEIP_LAUNCH_OK();
     return PDEIP_OK;
@@ -508,8 +547,10 @@ extern "C" int pdeip_kl_integrate_path(const float* z0, float* z_last, float* tr
                 PDEIP_ERR_INVALID_ARG, "unknown schedule %d", schedule);
   PDEIP_REQUIRE(state_layout == PDEIP_LAYOUT_AOS || state_layout == PDEIP_LAYOUT_SOA, PDEIP_ERR_INVALID_ARG,
                 "unknown state layout %d", state_layout);
-  PDEIP_REQUIRE(traj_layout >= 0 && traj_layout <= 2, PDEIP_ERR_INVALID_ARG, "unknown trajectory layout %d",
+  PDEIP_REQUIRE(traj_layout >= 0 && traj_layout <= 3, PDEIP_ERR_INVALID_ARG, "unknown trajectory layout %d",
                 traj_layout);
+  PDEIP_REQUIRE(traj_layout != PDEIP_TRAJ_BLOCK128 || traj == nullptr || n_particles % 128 == 0, PDEIP_ERR_INVALID_ARG,
+                "PDEIP_TRAJ_BLOCK128 needs n_particles %% 128 == 0 (got %lld)", (long long)n_particles);
   PDEIP_REQUIRE(emit_every >= 1 && emit_offset >= 0 && emit_offset < emit_every, PDEIP_ERR_INVALID_ARG,
                 "emit_every/emit_offset out of range");
   PDEIP_REQUIRE(drift_kind == PDEIP_DRIFT_NONE || drift_params != nullptr, PDEIP_ERR_INVALID_ARG,

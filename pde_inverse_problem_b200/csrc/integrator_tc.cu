@@ -65,11 +65,6 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&t);
 }
-// v = hi + lo, both bf16 (round to nearest twice): two packed words per pair
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf2(a, b);
-  lo = pack_bf2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-}
 __device__ __forceinline__ void tm_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -81,8 +76,18 @@ __device__ __forceinline__ void tm_ld16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int DP, int KP>
-__global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(const IntegrateArgs a, int* status) {
+// v = hi + lo, both bf16 (round to nearest twice), for two pairs at once
+__device__ __forceinline__ void split2(float2 ab, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf2(ab.x, ab.y);
+  const float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  const float2 r = __ffma2_rn(hf, make_float2(-1.f, -1.f), ab);
+  lo = pack_bf2(r.x, r.y);
+}
+
+// BLK = true: trajectory in PDEIP_TRAJ_BLOCK128 ([S][N/128][3d][128]: every store of a step is base + immediate);
+// false: PDEIP_TRAJ_TIME_SOA ([3d][S][N]).
+template <int DP, int KP, bool BLK, int MINB>
+__global__ void __launch_bounds__(128, MINB) kl_integrate_tc_kernel(const IntegrateArgs a, int* status) {
   using S = Cfg<DP, KP>;
   extern __shared__ __align__(128) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -148,16 +153,16 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
   const uint32_t mbar = smem_u32(mbar_p);
   const uint32_t sA = smem_u32(sm + S::O_A), sOnes = smem_u32(sm + S::O_ONES), sMuH = smem_u32(sm + S::O_MUH),
                  sMuL = smem_u32(sm + S::O_MUL), sBias = smem_u32(sm + S::O_BIAS);
+  uint8_t* const rowA = sm + S::O_A + (uint32_t)(tid & 7) * 16u;  // + (tid >> 3) * row-group bytes + chunk * 128
   uint32_t phase = 0;
 
-  // ---- state ---------------------------------------------------------------------------------------------------
-  const int64_t n = (int64_t)blockIdx.x * 128 + tid;
-  const bool valid = n < a.n;
+  // ---- state.  Rows past the end of a ragged last tile repeat the last particle (same id, same values written to
+  // the same addresses), so that no load or store in the step loop needs a predicate. ----------------------------
+  const int64_t n_raw = (int64_t)blockIdx.x * 128 + tid;
+  const int64_t n = n_raw < a.n ? n_raw : a.n - 1;
   const uint64_t pid = a.particle_offset + (uint64_t)n;
   float2 q[DP / 2], p[DP / 2];
-#pragma unroll
-  for (int i = 0; i < DP / 2; ++i) q[i] = p[i] = make_float2(0.f, 0.f);
-  if (valid) {
+  {
     const float4* z4 = reinterpret_cast<const float4*>(a.z0 + n * (2 * DP));
 #pragma unroll
     for (int i4 = 0; i4 < DP / 4; ++i4) {
@@ -168,8 +173,10 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
   }
   const float t0 = philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
   const int Sn = a.n_steps;
-  const int64_t plane = (int64_t)Sn * a.n;  // floats per component plane of the [3d][S][N] trajectory
-  float* o = a.traj + n;                    // sample 0, component 0 of this particle
+  // BLK: element (sample s, tile t, component c, lane l) at ((s T + t) 3d + c) 128 + l ; else c S N + s N + n
+  const int64_t plane = BLK ? 128 : (int64_t)Sn * a.n;               // floats between components of a sample
+  const int64_t sstride = BLK ? (int64_t)gridDim.x * (3 * DP * 128) : a.n;  // floats between samples
+  float* o = BLK ? a.traj + ((int64_t)blockIdx.x * (3 * DP) * 128 + tid) : a.traj + n;  // sample 0, component 0
   const float rcs = 1.0f / cs;
 
   auto wait_commit = [&]() {
@@ -201,20 +208,23 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
     const float dmp = 1.f - a.gamma * h;
 
     // (1) x -> [x_hi | x_lo] rows of the A tile
+    {
+      uint8_t* const row = rowA + (uint32_t)(tid >> 3) * S::RG_X;
 #pragma unroll
-    for (int cg = 0; cg < DP / 8; ++cg) {
-      uint4 hi, lo;
-      split_pair(q[4 * cg].x, q[4 * cg].y, hi.x, lo.x);
-      split_pair(q[4 * cg + 1].x, q[4 * cg + 1].y, hi.y, lo.y);
-      split_pair(q[4 * cg + 2].x, q[4 * cg + 2].y, hi.z, lo.z);
-      split_pair(q[4 * cg + 3].x, q[4 * cg + 3].y, hi.w, lo.w);
-      *reinterpret_cast<uint4*>(sm + S::O_A + chunk_off(tid, cg, S::RG_X)) = hi;
-      *reinterpret_cast<uint4*>(sm + S::O_A + chunk_off(tid, DP / 8 + cg, S::RG_X)) = lo;
+      for (int cg = 0; cg < DP / 8; ++cg) {
+        uint4 hi, lo;
+        split2(q[4 * cg], hi.x, lo.x);
+        split2(q[4 * cg + 1], hi.y, lo.y);
+        split2(q[4 * cg + 2], hi.z, lo.z);
+        split2(q[4 * cg + 3], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(row + cg * 128) = hi;
+        *reinterpret_cast<uint4*>(row + (DP / 8 + cg) * 128) = lo;
+      }
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (warp == 0 && elect_one()) {
+    if (warp == ((2 * s) & 3) && elect_one()) {  // the issuing duty rotates over the four warps
       fence_after_sync();
       mma_bf16(tbase, make_desc(sOnes, 128u, S::RG_ONES), make_desc(sBias, 128u, S::RG_BIAS), make_idesc(KP, 0, 0), 0u);
       gemm_kk(tbase, sA, S::RG_X, 0, sMuH, S::RG_MU, 0, DP, KP, 1u);   // x_hi . mu_hi
@@ -236,31 +246,38 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
 #pragma unroll
       for (int i = 0; i < 16; ++i) m = fmaxf(m, l[i]);
     }
-    float se = 0.f;
+    float2 se2 = make_float2(0.f, 0.f);
+    {
+      const float2 nm2 = make_float2(-m, -m);
+      uint8_t* const row = rowA + (uint32_t)(tid >> 3) * S::RG_W;
 #pragma unroll
-    for (int c = 0; c < KP / 16; ++c) {
-      float l[16];
-      tm_ld16(t_logit + 16 * c, l);
-      tm_wait_ld();
+      for (int c = 0; c < KP / 16; ++c) {
+        float l[16];
+        tm_ld16(t_logit + 16 * c, l);
+        tm_wait_ld();
+        float2 e[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) l[i] = ex2f(l[i] - m);
-      se += ((l[0] + l[1]) + (l[2] + l[3])) + ((l[4] + l[5]) + (l[6] + l[7])) + ((l[8] + l[9]) + (l[10] + l[11])) +
-            ((l[12] + l[13]) + (l[14] + l[15]));
+        for (int i = 0; i < 8; ++i) {
+          const float2 t = __fadd2_rn(make_float2(l[2 * i], l[2 * i + 1]), nm2);
+          e[i] = make_float2(ex2f(t.x), ex2f(t.y));
+          se2 = __fadd2_rn(se2, e[i]);
+        }
 #pragma unroll
-      for (int hcg = 0; hcg < 2; ++hcg) {
-        uint4 hi, lo;
-        split_pair(l[8 * hcg], l[8 * hcg + 1], hi.x, lo.x);
-        split_pair(l[8 * hcg + 2], l[8 * hcg + 3], hi.y, lo.y);
-        split_pair(l[8 * hcg + 4], l[8 * hcg + 5], hi.z, lo.z);
-        split_pair(l[8 * hcg + 6], l[8 * hcg + 7], hi.w, lo.w);
-        *reinterpret_cast<uint4*>(sm + S::O_A + chunk_off(tid, 2 * c + hcg, S::RG_W)) = hi;
-        *reinterpret_cast<uint4*>(sm + S::O_A + chunk_off(tid, KP / 8 + 2 * c + hcg, S::RG_W)) = lo;
+        for (int hcg = 0; hcg < 2; ++hcg) {
+          uint4 hi, lo;
+          split2(e[4 * hcg], hi.x, lo.x);
+          split2(e[4 * hcg + 1], hi.y, lo.y);
+          split2(e[4 * hcg + 2], hi.z, lo.z);
+          split2(e[4 * hcg + 3], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(row + (2 * c + hcg) * 128) = hi;
+          *reinterpret_cast<uint4*>(row + (KP / 8 + 2 * c + hcg) * 128) = lo;
+        }
       }
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (warp == 0 && elect_one()) {
+    if (warp == ((2 * s + 1) & 3) && elect_one()) {
       fence_after_sync();
       gemm_km(tbase + KP, sA, S::RG_W, 0, sMuH, S::RG_MU, 0, 0, KP, DP, 0u);   // e_hi . mu_hi
       gemm_km(tbase + KP, sA, S::RG_W, KP, sMuH, S::RG_MU, 0, 0, KP, DP, 1u);  // e_lo . mu_hi
@@ -271,11 +288,12 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
     kick(s, dmp, sq, DP / 8, DP / 4);  // second half of the noise while GEMM 2 runs
     wait_commit();
 
-    // (3) grad U = (x - A / (cs se)) / sigma^2 ; finish the step
-    const float rn = -rcs / se;
+    // (3) grad U = (x - A / (cs se)) / sigma^2 ; finish the step.  grad U belongs to the state emitted as sample
+    // s - 1; at s = 0 it is parked in sample 0's slot, which step 1 overwrites.
+    const float rn = -rcs / (se2.x + se2.y);
     const float2 rn2 = make_float2(rn, rn), is2 = make_float2(a.inv_sigma2, a.inv_sigma2);
     const float2 nh2 = make_float2(-h, -h), h2 = make_float2(h, h);
-    float* og = o - a.n + 2 * DP * plane;  // grad U at the state emitted as sample s - 1
+    float* og = (s == 0 ? o : o - sstride) + 2 * DP * plane;
 #pragma unroll
     for (int c = 0; c < DP / 16; ++c) {
       float acc[16];
@@ -285,28 +303,46 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
       for (int i = 0; i < 8; ++i) {
         const int k = 8 * c + i;
         const float2 g = __fmul2_rn(__ffma2_rn(make_float2(acc[2 * i], acc[2 * i + 1]), rn2, q[k]), is2);
-        if (s >= 1 && valid) {
-          __stcs(og + (int64_t)(2 * k) * plane, g.x);
-          __stcs(og + (int64_t)(2 * k + 1) * plane, g.y);
+        if constexpr (BLK) {
+          __stcs(og + (2 * k) * 128, g.x);
+          __stcs(og + (2 * k + 1) * 128, g.y);
+        } else {
+          __stcs(og, g.x);
+          __stcs(og + plane, g.y);
+          og += 2 * plane;
         }
         p[k] = __ffma2_rn(nh2, g, p[k]);
         q[k] = __ffma2_rn(h2, p[k], q[k]);
       }
     }
     if (s < Sn) {
-      if (valid) {
+      if constexpr (BLK) {
 #pragma unroll
         for (int i = 0; i < DP / 2; ++i) {
-          __stcs(o + (int64_t)(2 * i) * plane, q[i].x);
-          __stcs(o + (int64_t)(2 * i + 1) * plane, q[i].y);
-          __stcs(o + (int64_t)(DP + 2 * i) * plane, p[i].x);
-          __stcs(o + (int64_t)(DP + 2 * i + 1) * plane, p[i].y);
+          __stcs(o + (2 * i) * 128, q[i].x);
+          __stcs(o + (2 * i + 1) * 128, q[i].y);
+          __stcs(o + (DP + 2 * i) * 128, p[i].x);
+          __stcs(o + (DP + 2 * i + 1) * 128, p[i].y);
+        }
+      } else {
+        float* w = o;
+#pragma unroll
+        for (int i = 0; i < DP / 2; ++i) {
+          __stcs(w, q[i].x);
+          __stcs(w + plane, q[i].y);
+          w += 2 * plane;
+        }
+#pragma unroll
+        for (int i = 0; i < DP / 2; ++i) {
+          __stcs(w, p[i].x);
+          __stcs(w + plane, p[i].y);
+          w += 2 * plane;
         }
       }
-      o += a.n;
     }
+    o += sstride;
   }
-  if (valid) {
+  {
     float4* zl = reinterpret_cast<float4*>(a.z_last + n * (2 * DP));
 #pragma unroll
     for (int i4 = 0; i4 < DP / 4; ++i4) {
@@ -322,9 +358,15 @@ __global__ void __launch_bounds__(128, PDEIP_ITC_MINB) kl_integrate_tc_kernel(co
 template <int DP, int KP>
 static int launch(const IntegrateArgs& a, int* status, cudaStream_t st) {
   using S = Cfg<DP, KP>;
-  auto kern = kl_integrate_tc_kernel<DP, KP>;
-  PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
   const int64_t grid = (a.n + 127) / 128;
+  const char* mb = getenv("PDEIP_ITC_MINB");  // tuning knob: CTAs per SM the register budget is sized for
+  const bool four = mb ? (mb[0] == '4') : (PDEIP_ITC_MINB == 4);
+  void (*kern)(const IntegrateArgs, int*);
+  if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
+    kern = four ? kl_integrate_tc_kernel<DP, KP, true, 4> : kl_integrate_tc_kernel<DP, KP, true, 3>;
+  else
+    kern = four ? kl_integrate_tc_kernel<DP, KP, false, 4> : kl_integrate_tc_kernel<DP, KP, false, 3>;
+  PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
   kern<<<(unsigned)grid, 128, S::TOTAL, st>>>(a, status);
   PDEIP_LAUNCH_OK();
   return PDEIP_OK;

@@ -39,7 +39,9 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
   const float u1 = ((float)(xa >> 8) + 1.0f) * 5.9604644775390625e-08f;  // 2^-24
   const float u2 = (float)(xb >> 8) * 5.9604644775390625e-08f;
-  const float r = sqrtf(-2.0f * __logf(u1));
+  float l2, r;  // r = sqrt(-2 ln u1) on two MUFU ops (lg2, sqrt), no slow-path branch
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2 * -1.3862943611198906f));
   float s, c;
   __sincosf(3.14159265358979323846f * (2.0f * u2 - 1.0f), &s, &c);
   n0 = r * c;

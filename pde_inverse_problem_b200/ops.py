@@ -74,7 +74,9 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
     if want_traj:
         width = two_d + d if emit_drift else two_d
         shape = {L.TRAJ_PARTICLE_MAJOR: (n, s_emit, width), L.TRAJ_TIME_MAJOR: (s_emit, n, width),
-                 L.TRAJ_TIME_SOA: (width, s_emit, n)}[traj_layout]
+                 L.TRAJ_TIME_SOA: (width, s_emit, n), L.TRAJ_BLOCK128: (s_emit, n // 128, width, 128)}[traj_layout]
+        if traj_layout == L.TRAJ_BLOCK128 and n % 128:
+            raise PdeipError(f"TRAJ_BLOCK128 needs n % 128 == 0, got n={n}")
         if traj_out is not None:
             if traj_out.numel() < n * s_emit * width:
                 raise PdeipError("traj_out too small")
@@ -274,6 +276,10 @@ class ResidualAccumulator:
                 if points.ndim != 2 or points.shape[1] != dim:
                     raise PdeipError(f"points must be [n,{dim}], got {tuple(points.shape)}")
                 n_points = points.shape[0]
+            elif layout == L.LAYOUT_BLOCK128:
+                if points.ndim != 3 or tuple(points.shape[1:]) != (dim, 128):
+                    raise PdeipError(f"points must be [n/128,{dim},128], got {tuple(points.shape)}")
+                n_points = points.shape[0] * 128
             else:
                 if points.ndim != 2 or points.shape[0] != dim:
                     raise PdeipError(f"points must be [{dim},n], got {tuple(points.shape)}")

@@ -78,12 +78,20 @@ class HotPath:
             else:
                 zc = self.z_stage[:nc]
                 zc.copy_(z0[lo:hi], non_blocking=True)
+            # 128-point blocks of component planes when the chunk allows it (every store of an integrator step and
+            # every load of a residual tile is base + constant), else component planes over the whole chunk
+            blocked = nc % 128 == 0
             z_last, traj, _ = ops.kl_integrate(
                 zc, c.n_steps, dt, c.gamma, c.drift_kind, self.drift_params, n_gaussian=c.n_gaussian, sigma=c.sigma,
-                seed=seed, particle_offset=particle_offset + lo, traj_layout=L.TRAJ_TIME_SOA,
+                seed=seed, particle_offset=particle_offset + lo,
+                traj_layout=L.TRAJ_BLOCK128 if blocked else L.TRAJ_TIME_SOA,
                 emit_every=c.emit_every, traj_out=self.traj, z_last_out=self.z_last[:nc], emit_drift=True, path=c.path)
-            self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * c.d, self.s_emit * nc), w_0T, coef=c.gamma,
-                                layout=L.LAYOUT_SOA, true_grad=self.true_in_points, path=c.path)
+            if blocked:
+                self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(self.s_emit * nc // 128, 3 * c.d, 128), w_0T,
+                                    coef=c.gamma, layout=L.LAYOUT_BLOCK128, true_grad=self.true_in_points, path=c.path)
+            else:
+                self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * c.d, self.s_emit * nc), w_0T, coef=c.gamma,
+                                    layout=L.LAYOUT_SOA, true_grad=self.true_in_points, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, z_last, w_b, coef=2.0 / c.total_time, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, zc, w_b, coef=-2.0 / c.total_time, path=c.path)
         sums, grad = self.acc.finalize()

@@ -280,8 +280,15 @@ def test_fast_production_kernel_matches_generic_kernel(cuda, drift, d, K):
     assert relmax(zl_fast, zl_ref) < 5e-5
 
 
+def unblock(tr):
+    """[S][n/128][C][128] (TRAJ_BLOCK128) -> [C][S][n] (TRAJ_TIME_SOA)"""
+    S, nb, C, _ = tr.shape
+    return tr.permute(2, 0, 1, 3).reshape(C, S, nb * 128)
+
+
 @pytest.mark.parametrize("d,K,n,S", [(32, 64, 4096 + 37, 12), (32, 64, 300, 200), (32, 40, 1000, 12), (32, 7, 129, 12),
-                                     (16, 16, 1000, 12), (16, 64, 2048, 12), (16, 33, 515, 50)])
+                                     (16, 16, 1000, 12), (16, 64, 2048, 12), (16, 33, 515, 50), (32, 64, 4096, 12),
+                                     (16, 48, 640, 30)])
 def test_tensor_core_gmm_integrator_matches_fp32_kernel(cuda, d, K, n, S):
     """pdeip_kl_integrate_path(PDEIP_PATH_TENSOR): particle x centre contraction and softmax-weighted centre sum on
     tcgen05 with bf16 hi + lo split operands, against the fp32 production kernel on the same Philox stream.
@@ -302,6 +309,12 @@ def test_tensor_core_gmm_integrator_matches_fp32_kernel(cuda, d, K, n, S):
     zl_t, tr_t = run(L.PATH_TENSOR)
     assert ops.tensor_path_status() == 0
     zl_f, tr_f = run(L.PATH_FP32)
+    if n % 128 == 0:  # the blocked trajectory layout holds the same numbers
+        for path, zl_s, tr_s in ((L.PATH_TENSOR, zl_t, tr_t), (L.PATH_FP32, zl_f, tr_f)):
+            zl_b, tr_b, _ = ops.kl_integrate(z0, S, T / S, gamma, L.DRIFT_GMM, mus, n_gaussian=K, seed=99,
+                                             particle_offset=12345, traj_layout=L.TRAJ_BLOCK128, emit_drift=True, path=path)
+            assert tr_b.shape == (S, n // 128, 3 * d, 128)
+            assert torch.equal(unblock(tr_b), tr_s) and torch.equal(zl_b, zl_s)
     assert tr_t.shape == tr_f.shape == (3 * d, S, n)
     assert torch.isfinite(tr_t).all() and torch.isfinite(zl_t).all()
     # one step from identical states, then the emitted grad U of sample 0 (evaluated at step 1)
@@ -313,3 +326,37 @@ def test_tensor_core_gmm_integrator_matches_fp32_kernel(cuda, d, K, n, S):
     x = tr_t[:d, S // 2].t().double().cpu()
     gref = o_pot.vg_gmm_V(x, mus.double().cpu(), 1.0)
     assert relmax(tr_t[2 * d:, S // 2].t(), gref) < 2e-4
+
+
+@pytest.mark.parametrize("drift,d,K", [("gmm", 8, 16), ("linear", 4, 0), ("linear", 16, 0), ("gmm", 32, 64)])
+def test_block128_trajectory_layout(cuda, drift, d, K):
+    """PDEIP_TRAJ_BLOCK128 ([S][N/128][3d][128]) carries exactly the numbers of PDEIP_TRAJ_TIME_SOA, from the
+    production kernel and from the generic kernel; a ragged N is refused."""
+    import os
+    from pde_inverse_problem_b200 import ops, _lib as L
+    n, S, T, gamma = 1024, 9, 0.18, 0.5
+    g = torch.Generator().manual_seed(3 + d)
+    z0 = torch.randn(n, 2 * d, generator=g).to(cuda)
+    if drift == "gmm":
+        params, kind = (torch.rand(K, d, generator=g) * 8 - 4).to(cuda), L.DRIFT_GMM
+    else:
+        f = torch.randn(d, d + 1, generator=g)
+        params, kind = ((f @ f.T) / d).to(cuda), L.DRIFT_LINEAR
+
+    def run(layout, nn=n):
+        zl, tr, _ = ops.kl_integrate(z0[:nn], S, T / S, gamma, kind, params, n_gaussian=K, seed=5, traj_layout=layout,
+                                     emit_drift=True)
+        torch.cuda.synchronize()
+        return zl.clone(), tr.clone()
+
+    for generic in (False, True):
+        if generic:
+            os.environ["PDEIP_NO_FAST_INTEGRATOR"] = "1"
+        try:
+            zl_s, tr_s = run(L.TRAJ_TIME_SOA)
+            zl_b, tr_b = run(L.TRAJ_BLOCK128)
+        finally:
+            os.environ.pop("PDEIP_NO_FAST_INTEGRATOR", None)
+        assert torch.equal(unblock(tr_b), tr_s) and torch.equal(zl_b, zl_s)
+    with pytest.raises(Exception):
+        run(L.TRAJ_BLOCK128, nn=n - 1)

@@ -133,3 +133,25 @@ def test_tensor_path_edge_sizes(cuda, n):
         return
     assert relmax(stc[L.SUM_LOSS], s32[L.SUM_LOSS]) < TOL
     assert relmax(gtc, g32) < 2 * TOL
+
+
+@pytest.mark.parametrize("path_name,d", [("fp32", 8), ("tensor", 8), ("tensor", 32), ("fp32", 16)])
+def test_block128_point_layout(cuda, path_name, d):
+    """PDEIP_LAYOUT_BLOCK128 ([n/128][dim][128], what the integrator emits with PDEIP_TRAJ_BLOCK128) gives bit-identical
+    sums and gradient to the SoA layout of the same points; a ragged n is refused."""
+    ops, L = _ops()
+    n = 128 * 75
+    path = L.PATH_FP32 if path_name == "fp32" else L.PATH_TENSOR
+    flat = o_model.flatten_params(_params(d)).float().to(cuda)
+    g = torch.Generator().manual_seed(40 + d)
+    pts3 = (torch.randn(n, 3 * d, generator=g) * 1.3).to(cuda)  # [x, v, grad V_true]
+    spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
+    tg = ops.TrueGrad(L.DRIFT_IN_POINTS)
+    s_s, g_s = _run(ops, L, cuda, spec, flat, pts3.t().contiguous(), n, 0.5, tg, path, layout=L.LAYOUT_SOA)
+    blk = pts3.view(n // 128, 128, 3 * d).permute(0, 2, 1).contiguous()
+    s_b, g_b = _run(ops, L, cuda, spec, flat, blk, n, 0.5, tg, path, layout=L.LAYOUT_BLOCK128)
+    assert torch.equal(s_b, s_s) and torch.equal(g_b, g_s)
+    acc = ops.ResidualAccumulator(spec, device=cuda).begin()
+    with pytest.raises(Exception):
+        acc.accumulate(L.SET_KFP_0T, flat, blk, 1.0 / n, coef=0.5, true_grad=tg, path=path, layout=L.LAYOUT_BLOCK128,
+                       n_points=n - 5)

@@ -7,6 +7,7 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 path = L.PATH_TENSOR if (len(sys.argv) > 3 and sys.argv[3] == "tensor") else L.PATH_FP32
 n = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 18 if d <= 8 else 75776)
 S = 200
+blk = len(sys.argv) > 5 and sys.argv[5] == "block"
 dev = torch.device('cuda')
 z0 = torch.randn(n, 2 * d, device=dev)
 if K > 0:
@@ -16,7 +17,7 @@ else:
 traj = torch.empty(3 * d * S * n, device=dev)
 zl = torch.empty_like(z0)
 def run():
-    ops.kl_integrate(z0, S, 0.01, 0.5, kind, params, n_gaussian=K, seed=1, traj_layout=L.TRAJ_TIME_SOA, traj_out=traj,
+    ops.kl_integrate(z0, S, 0.01, 0.5, kind, params, n_gaussian=K, seed=1, traj_layout=L.TRAJ_BLOCK128 if blk else L.TRAJ_TIME_SOA, traj_out=traj,
                      z_last_out=zl, emit_drift=True, path=path)
 for _ in range(3): run()
 torch.cuda.synchronize()
@@ -25,4 +26,4 @@ e0.record()
 for _ in range(5): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"d={d} K={K} n={n} path={'tensor' if path else 'fp32'} status={ops.tensor_path_status()}: {ms:.3f} ms  {n*(S+1)/ms*1e3:.3e} particle-steps/s  {n*S*3*d*4/ms/1e6:.0f} GB/s")
+print(f"d={d} K={K} n={n} path={'tensor' if path else 'fp32'} layout={'block128' if blk else 'time_soa'} minb={os.environ.get('PDEIP_ITC_MINB', '-')} status={ops.tensor_path_status()}: {ms:.3f} ms  {n*(S+1)/ms*1e3:.3e} particle-steps/s  {n*S*3*d*4/ms/1e6:.0f} GB/s")
