@@ -36,11 +36,11 @@ WORKLOADS = {
     "C2": dict(name="KOU d=4 N=2^20 S=100 (kinetic OU, scripts/run_KOU.sh)", d=4, K=0, n=1 << 20, S=100, T=2.0,
                gamma=1.0, chunk=1 << 19),
     "C3": dict(name="KGMM d=8 K=16 N=2^22 S=200 (scripts/run_KGMM.sh)", d=8, K=16, n=1 << 22, S=200, T=2.0,
-               gamma=0.5, chunk=1 << 18),
+               gamma=0.5, chunk=3 * 75776),  # chunk = whole waves of the integrator grid (148 SMs x 4 CTAs x 128 particles)
     "C4": dict(name="KMV-quadratic (-A x drift) d=16 N=2^22 S=100", d=16, K=0, n=1 << 22, S=100, T=2.0,
                gamma=1.0, chunk=1 << 18),
     "C5": dict(name="KGMM d=32 K=64 N=2^21/rank S=200 (2^24 over 8 ranks)", d=32, K=64, n=1 << 21, S=200, T=2.0,
-               gamma=0.5, chunk=1 << 16),
+               gamma=0.5, chunk=56832),  # 148 SMs x 3 CTAs x 128 particles: one full wave of the tcgen05 integrator
 }
 HIDDEN, LAYERS, OUT = 32, 2, 40
 
@@ -166,25 +166,10 @@ def run_ours(args):
 
     # ---- phase timing helpers (events on torch's current stream, the stream the kernels launch on) --------
     def timed_phases(seed):
-        """One step with CUDA events around the integrator and residual launches of every chunk."""
+        """One more step of the same pipeline with CUDA events around the integrator and 0T-residual launches of
+        every chunk (no optimizer update: the parameters of the timed steps are not touched)."""
         ev = []
-        dt = cfg.total_time / cfg.n_steps
-        flat = model.flat(params)
-        hp.acc.begin()
-        for lo in range(0, n, cfg.chunk):
-            hi = min(n, lo + cfg.chunk)
-            nc = hi - lo
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record()
-            z_last, traj, _ = ops.kl_integrate(z0[lo:hi], S, dt, cfg.gamma, drift_kind, drift, n_gaussian=K,
-                                               seed=seed, particle_offset=offset + lo, traj_layout=L.TRAJ_TIME_SOA,
-                                               traj_out=hp.traj, z_last_out=hp.z_last[:nc], emit_drift=True)
-            e[1].record()
-            hp.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * d, hp.s_emit * nc), 1.0 / (n_global * hp.s_emit),
-                              coef=cfg.gamma, layout=L.LAYOUT_SOA, true_grad=hp.true_in_points, path=path)
-            e[2].record()
-            ev.append(e)
-        hp.acc.finalize()
+        hp.step(z0, seed=seed, n_global=n_global, particle_offset=offset, apply_optimizer=False, phase_events=ev)
         torch.cuda.synchronize()
         t_int = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
         t_res = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
@@ -262,7 +247,8 @@ def run_ours(args):
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": shard.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if path == L.PATH_FP32 else "bf16 GEMM operands (weights and x split hi+lo), f32 accumulate / epilogue / integrator",
+            "dtype": "f32" if path == L.PATH_FP32 else ("bf16 GEMM operands split hi+lo (MLP weights and x; GMM centres, x and softmax weights "
+                                                      "in the integrator at d >= 16), f32 accumulate / epilogue / state"),
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
                        "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
@@ -281,7 +267,9 @@ def run_ours(args):
                          "peak_source": pk["src"] + " bf16 sustained",
                          "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval},
             "kernels": {
-                "kl_integrate": {"bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                "kl_integrate": {"kernel": ("kl_integrate_tc_kernel (GMM contraction on tcgen05)"
+                                            if path == L.PATH_TENSOR and K > 0 and d in (16, 32) and K <= 64
+                                            else "kl_integrate_fast_kernel (fp32)"), "bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": int_gbs / pk["hbm"], "particle_steps_per_s_per_gpu": int_rate,
                                  "bytes_per_emitted_step": 3 * d * 4, "ms_per_step": t_int * 1e3},
                 "mlp_residual": {"ms_per_step": t_res * 1e3, "evals_per_s_per_gpu": res_rate},

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
 #pragma unroll
     for (int j = 0; j < DP / 4; ++j) {
       float r4[4];
-      philox_normal4(a.seed, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
+      philox_normal4_rk(a.rk, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
       const float2 xa = make_float2(r4[0], r4[1]), xb = make_float2(r4[2], r4[3]);
       // same association as the generic kernel up to the fused damping factor (1 - gamma h)
       float2 pa = __ffma2_rn(nh2, g[2 * j], __fmul2_rn(p[2 * j], dmp2));
@@ -566,6 +566,7 @@ extern "C" int pdeip_kl_integrate_path(const float* z0, float* z_last, float* tr
   a.step_offset = step_offset; a.schedule = schedule; a.state_layout = state_layout;
   a.traj_layout = traj_layout; a.emit_every = emit_every; a.emit_offset = emit_offset;
   a.emit_drift = emit_drift ? 1 : 0;
+  a.rk = philox_round_keys(seed);
   const int n_samples = n_steps;  // both schedules expose n_steps samples
   a.s_emit = (n_samples - emit_offset + emit_every - 1) / emit_every;
   cudaStream_t st = (cudaStream_t)stream;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace pdeip {
 
 struct IntegrateArgs {
@@ -31,6 +33,7 @@ struct IntegrateArgs {
   int emit_offset;
   int s_emit;  // number of emitted samples
   int emit_drift;  // 1: every emitted sample carries grad U(x) as components [2d, 3d)
+  PhiloxRoundKeys rk;  // round keys of `seed`
 };
 
 // integrator_tc.cu: GMM drift on the tensor cores (PDEIP_PATH_TENSOR)

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128, MINB) kl_integrate_tc_kernel(const Integr
 #pragma unroll
     for (int j = j0; j < j1; ++j) {
       float r4[4];
-      philox_normal4(a.seed, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
+      philox_normal4_rk(a.rk, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
       p[2 * j] = __ffma2_rn(sq2, make_float2(r4[0], r4[1]), __fmul2_rn(p[2 * j], dmp2));
       p[2 * j + 1] = __ffma2_rn(sq2, make_float2(r4[2], r4[3]), __fmul2_rn(p[2 * j + 1], dmp2));
     }

@@ -58,10 +58,11 @@ class HotPath:
         return n * self.s_emit
 
     def step(self, z0: torch.Tensor, seed: int, n_global: Optional[int] = None, particle_offset: int = 0,
-             apply_optimizer: bool = True) -> Dict[str, torch.Tensor]:
+             apply_optimizer: bool = True, phase_events: Optional[list] = None) -> Dict[str, torch.Tensor]:
         """One iteration over the local ensemble z0 [n, 2d] (CUDA, or pinned host memory: then each chunk is
         copied host->device inside the step).  n_global: ensemble size over all ranks (weights are 1/global
-        counts so shards add up under one all-reduce)."""
+        counts so shards add up under one all-reduce).  phase_events: if a list, three CUDA events per chunk are
+        appended to it (before the integrator, between integrator and 0T residual, after the 0T residual)."""
         c = self.cfg
         n = z0.shape[0]
         n_global = n if n_global is None else n_global
@@ -81,17 +82,25 @@ class HotPath:
             # 128-point blocks of component planes when the chunk allows it (every store of an integrator step and
             # every load of a residual tile is base + constant), else component planes over the whole chunk
             blocked = nc % 128 == 0
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if phase_events is not None else None
+            if ev:
+                ev[0].record()
             z_last, traj, _ = ops.kl_integrate(
                 zc, c.n_steps, dt, c.gamma, c.drift_kind, self.drift_params, n_gaussian=c.n_gaussian, sigma=c.sigma,
                 seed=seed, particle_offset=particle_offset + lo,
                 traj_layout=L.TRAJ_BLOCK128 if blocked else L.TRAJ_TIME_SOA,
                 emit_every=c.emit_every, traj_out=self.traj, z_last_out=self.z_last[:nc], emit_drift=True, path=c.path)
+            if ev:
+                ev[1].record()
             if blocked:
                 self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(self.s_emit * nc // 128, 3 * c.d, 128), w_0T,
                                     coef=c.gamma, layout=L.LAYOUT_BLOCK128, true_grad=self.true_in_points, path=c.path)
             else:
                 self.acc.accumulate(L.SET_KFP_0T, flat, traj.view(3 * c.d, self.s_emit * nc), w_0T, coef=c.gamma,
                                     layout=L.LAYOUT_SOA, true_grad=self.true_in_points, path=c.path)
+            if ev:
+                ev[2].record()
+                phase_events.append(ev)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, z_last, w_b, coef=2.0 / c.total_time, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, zc, w_b, coef=-2.0 / c.total_time, path=c.path)
         sums, grad = self.acc.finalize()
