@@ -52,6 +52,16 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// the same address as base + c * stride: hoists the layout switch out of per-component loops
+__device__ __forceinline__ int64_t point_base(int layout, int64_t n, int dim) {
+  if (layout == PDEIP_LAYOUT_BLOCK128) return (n >> 7) * ((int64_t)dim * 128) + (n & 127);
+  return layout == PDEIP_LAYOUT_AOS ? n * dim : n;
+}
+__device__ __forceinline__ int64_t comp_stride(int layout, int64_t n_total) {
+  if (layout == PDEIP_LAYOUT_BLOCK128) return 128;
+  return layout == PDEIP_LAYOUT_AOS ? 1 : n_total;
+}
+
 // element (point n, component c) of a [n][dim] (AOS), [dim][n] (SOA) or [n/128][dim][128] (BLOCK128) array
 __device__ __forceinline__ int64_t elem_index(int layout, int64_t n, int c, int64_t n_total, int dim) {
   if (layout == PDEIP_LAYOUT_BLOCK128) return ((n >> 7) * dim + c) * 128 + (n & 127);

@@ -606,8 +606,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     constexpr int NI = (3 * S::XC + 1) / 2;
     float xin0[NI][8], xin1[NI][8];
     auto load_into = [&](float (&xin)[NI][8], int64_t t) {
+      const int64_t cstride = comp_stride(a.layout, a.n_points);
       const int64_t pp = t * 128 + row;
       const int64_t pc = (t < n_tiles && pp < a.n_points) ? pp : 0;
+      const float* const pbase = a.points + point_base(a.layout, pc, dimw);
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int j = half + 2 * i;
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         for (int e = 0; e < 8; ++e) {
           const int u = cg * 8 + e;
           const int uc = u < d ? u : 0;
-          xin[i][e] = __ldg(a.points + elem_index(a.layout, pc, bandc * d + uc, a.n_points, dimw));
+          xin[i][e] = __ldg(pbase + (bandc * d + uc) * cstride);
         }
       }
     };
