@@ -49,7 +49,12 @@ class HotPath:
         self.traj = torch.empty(3 * cfg.d * s_emit * cfg.chunk, device=self.device, dtype=torch.float32)
         self.true_in_points = ops.TrueGrad(L.DRIFT_IN_POINTS)
         self.z_last = torch.empty((cfg.chunk, 2 * cfg.d), device=self.device, dtype=torch.float32)
-        self.z_stage = torch.empty((cfg.chunk, 2 * cfg.d), device=self.device, dtype=torch.float32)
+        # host-resident ensembles: two staging buffers and a copy stream, so that chunk k+1 crosses PCIe / NVLink-C2C
+        # while chunk k is integrated
+        self.z_stage = [torch.empty((cfg.chunk, 2 * cfg.d), device=self.device, dtype=torch.float32) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.stage_ready = [torch.cuda.Event() for _ in range(2)]  # H2D of the buffer finished
+        self.stage_free = [torch.cuda.Event() for _ in range(2)]   # last kernel reading the buffer finished
 
     def particle_steps(self, n: int) -> int:
         return n * (self.cfg.n_steps + 1)  # the reference does S+1 update_steps per trajectory
@@ -71,14 +76,30 @@ class HotPath:
         w_0T = 1.0 / (n_global * self.s_emit)
         w_b = 1.0 / n_global
         self.acc.begin()
-        for lo in range(0, n, c.chunk):
+        main = torch.cuda.current_stream(self.device)
+        staged = not z0.is_cuda
+
+        def prefetch(k: int):  # H2D of chunk k into staging buffer k % 2 on the copy stream
+            a, b = k * c.chunk, min(n, (k + 1) * c.chunk)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.stage_free[k % 2])
+                self.z_stage[k % 2][: b - a].copy_(z0[a:b], non_blocking=True)
+                self.stage_ready[k % 2].record(self.copy_stream)
+
+        if staged:
+            for ev in self.stage_free:
+                ev.record(main)  # whatever used the buffers before this step is ordered before the first copies
+            prefetch(0)
+        for k, lo in enumerate(range(0, n, c.chunk)):
             hi = min(n, lo + c.chunk)
             nc = hi - lo
-            if z0.is_cuda:
+            if not staged:
                 zc = z0[lo:hi]
             else:
-                zc = self.z_stage[:nc]
-                zc.copy_(z0[lo:hi], non_blocking=True)
+                if hi < n:
+                    prefetch(k + 1)
+                main.wait_event(self.stage_ready[k % 2])
+                zc = self.z_stage[k % 2][:nc]
             # 128-point blocks of component planes when the chunk allows it (every store of an integrator step and
             # every load of a residual tile is base + constant), else component planes over the whole chunk
             blocked = nc % 128 == 0
@@ -103,6 +124,8 @@ class HotPath:
                 phase_events.append(ev)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, z_last, w_b, coef=2.0 / c.total_time, path=c.path)
             self.acc.accumulate(L.SET_KFP_BOUNDARY, flat, zc, w_b, coef=-2.0 / c.total_time, path=c.path)
+            if staged:
+                self.stage_free[k % 2].record(main)
         sums, grad = self.acc.finalize()
         shard = parallel.Shard.current()
         if shard.world > 1:

@@ -56,12 +56,11 @@ def test_c2_kinetic_ou_2e20_particles_match_analytic_moments(cuda):
     assert abs(rel_c - gap) < 6e-3      # same statistical error / same O(dt) bias as the reference scheme
 
 
-def _hot_path(cuda, path, chunk, n, offset=0, n_global=None, seed=3):
+def _hot_path(cuda, path, chunk, n, offset=0, n_global=None, seed=3, d=8, K=16, S=40, host=False):
     import math
     from pde_inverse_problem_b200 import ops, _lib as L
     from pde_inverse_problem_b200.core.model import V_hypothesis
     from pde_inverse_problem_b200.pipeline import HotPath, HotPathConfig
-    d, K, S = 8, 16, 40
     g = torch.Generator().manual_seed(1)
     mus = (torch.rand(K, d, generator=g) * 8 - 4).to(cuda)
     model = V_hypothesis(1, [32, 32], d)
@@ -71,6 +70,10 @@ def _hot_path(cuda, path, chunk, n, offset=0, n_global=None, seed=3):
     hp = HotPath(cfg, model, params, mus, ops.TrueGrad(L.DRIFT_GMM, mus, 1.0), optimizer=None, device=cuda)
     cov_half = torch.diag(torch.cat([torch.full((d,), 2.0), torch.full((d,), math.sqrt(0.1))])).to(cuda)
     z0 = ops.gaussian_sample(n, 2 * d, None, cov_half, seed=7, particle_offset=offset, device=cuda)
+    if host:  # ensemble in pinned host memory: chunks are staged host -> device inside the step (double-buffered)
+        zh = torch.empty((n, 2 * d), dtype=torch.float32, pin_memory=True)
+        zh.copy_(z0)
+        z0 = zh
     out = hp.step(z0, seed=seed, n_global=n_global or n, particle_offset=offset, apply_optimizer=False)
     torch.cuda.synchronize()
     return out["sums"].double().cpu(), out["grad"].double().cpu()
@@ -102,3 +105,29 @@ def test_pipeline_shards_add_up(cuda):
     sb, gb = _hot_path(cuda, L.PATH_TENSOR, 1 << 12, n // 2, offset=n // 2, n_global=n)
     assert relmax((sa + sb)[L.SUM_LOSS], s_all[L.SUM_LOSS]) < 1e-4
     assert relmax(ga + gb, g_all) < 1e-4
+
+
+def test_pipeline_host_resident_ensemble_and_ragged_chunks(cuda):
+    """The e2e configuration of bench.py (ensemble in pinned host memory, chunks copied on a side stream while the
+    previous chunk is integrated) gives bit-identical sums and gradient to the device-resident run; a chunk size that
+    is not a multiple of 128 (component-plane trajectory instead of 128-point blocks) agrees to rounding."""
+    from pde_inverse_problem_b200 import _lib as L
+    n = 1 << 14
+    s_dev, g_dev = _hot_path(cuda, L.PATH_TENSOR, 1 << 12, n)
+    s_host, g_host = _hot_path(cuda, L.PATH_TENSOR, 1 << 12, n, host=True)
+    assert torch.equal(s_dev, s_host) and torch.equal(g_dev, g_host)
+    s_rag, g_rag = _hot_path(cuda, L.PATH_TENSOR, 5000, n, host=True)
+    assert relmax(s_rag[L.SUM_LOSS], s_dev[L.SUM_LOSS]) < 1e-4
+    assert relmax(g_rag, g_dev) < 1e-4
+
+
+def test_pipeline_c5_shape_tensor_integrator_matches_fp32(cuda):
+    """C5-shaped iteration (d = 32, K = 64): integrator GMM contraction on tcgen05 + tcgen05 residual against the
+    all-fp32 pipeline, tolerance class "bf16 GEMM paths" (1e-2)."""
+    from pde_inverse_problem_b200 import _lib as L
+    n = 1 << 12
+    s32, g32 = _hot_path(cuda, L.PATH_FP32, 1 << 11, n, d=32, K=64, S=20)
+    stc, gtc = _hot_path(cuda, L.PATH_TENSOR, 1 << 11, n, d=32, K=64, S=20)
+    assert relmax(stc[L.SUM_LOSS], s32[L.SUM_LOSS]) < 1e-2
+    assert relmax(stc[L.SUM_GT], s32[L.SUM_GT]) < 1e-2
+    assert relmax(gtc, g32) < 1e-2
