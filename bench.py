@@ -36,7 +36,7 @@ WORKLOADS = {
     "C2": dict(name="KOU d=4 N=2^20 S=100 (kinetic OU, scripts/run_KOU.sh)", d=4, K=0, n=1 << 20, S=100, T=2.0,
                gamma=1.0, chunk=1 << 19),
     "C3": dict(name="KGMM d=8 K=16 N=2^22 S=200 (scripts/run_KGMM.sh)", d=8, K=16, n=1 << 22, S=200, T=2.0,
-               gamma=0.5, chunk=3 * 75776),  # chunk = whole waves of the integrator grid (148 SMs x 4 CTAs x 128 particles)
+               gamma=0.5, chunk=303104),  # two whole waves of the tcgen05 integrator grid (148 SMs x 8 CTAs x 128 particles)
     "C4": dict(name="KMV-quadratic (-A x drift) d=16 N=2^22 S=100", d=16, K=0, n=1 << 22, S=100, T=2.0,
                gamma=1.0, chunk=1 << 18),
     "C5": dict(name="KGMM d=32 K=64 N=2^21/rank S=200 (2^24 over 8 ranks)", d=32, K=64, n=1 << 21, S=200, T=2.0,
@@ -248,7 +248,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if path == L.PATH_FP32 else ("bf16 GEMM operands split hi+lo (MLP weights and x; GMM centres, x and softmax weights "
-                                                      "in the integrator at d >= 16), f32 accumulate / epilogue / state"),
+                                                      "in the integrator), f32 accumulate / epilogue / state"),
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
                        "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
@@ -268,7 +268,7 @@ def run_ours(args):
                          "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval},
             "kernels": {
                 "kl_integrate": {"kernel": ("kl_integrate_tc_kernel (GMM contraction on tcgen05)"
-                                            if path == L.PATH_TENSOR and K > 0 and d in (16, 32) and K <= 64
+                                            if path == L.PATH_TENSOR and K > 0 and d in (8, 16, 32) and K <= 64
                                             else "kl_integrate_fast_kernel (fp32)"), "bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": int_gbs / pk["hbm"], "particle_steps_per_s_per_gpu": int_rate,
                                  "bytes_per_emitted_step": 3 * d * 4, "ms_per_step": t_int * 1e3},

@@ -116,7 +116,7 @@ int pdeip_kl_integrate(const float* z0, float* z_last, float* traj, float* tau,
 
 /* Same call with a kernel path.  PDEIP_PATH_FP32: CUDA-core fp32 arithmetic throughout (rtol 1e-5 class).
  * PDEIP_PATH_TENSOR: in the production configuration (Philox noise, REFERENCE schedule, AOS state, TIME_SOA
- * trajectory with emit_drift, emit_every 1) with the GMM drift, d = 16 or 32 and n_gaussian <= 64, the particle x
+ * trajectory with emit_drift, emit_every 1) with the GMM drift, d = 8, 16 or 32 and n_gaussian <= 64, the particle x
  * centre contraction and the softmax-weighted centre sum run on tcgen05 with bf16 hi + lo split operands
  * ("bf16 GEMM path", rtol 1e-2 class; measured ~1e-4); every other configuration runs the fp32 kernels. */
 int pdeip_kl_integrate_path(const float* z0, float* z_last, float* traj, float* tau,

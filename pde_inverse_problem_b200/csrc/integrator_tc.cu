@@ -355,6 +355,245 @@ __global__ void __launch_bounds__(128, MINB) kl_integrate_tc_kernel(const Integr
   if (warp == 0) tmem_dealloc(tbase, S::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// d = 8 (C3: K = 16).  Same step, operands packed so that every MMA has a full K = 16:
+//   A tile [128][32]  = [x_hi | x_lo | x_hi | 1 1 1 0 0 0 0 0]          B tile [K][32] = [mu~_hi | mu~_hi | mu~_lo | b0 b1 b2 0..]
+//   GEMM 1  L[128 x K]  = A . B^T                                       (two MMAs)
+//   GEMM 2  Acc[128 x 16] = e_hi . B[:, 0:16] + e_lo . B[:, 0:16] + e_hi . B[:, 16:32]   (MN-major views of the B tile;
+//           columns 0..7 of Acc are sum_k e_k mu~_k, columns 8..15 are never read)
+// ------------------------------------------------------------------------------------------------------------
+template <int KP>
+struct Cfg8 {
+  static_assert(KP % 16 == 0 && KP >= 16 && KP <= 64, "padded centre count: multiple of 16, <= 64");
+  static constexpr uint32_t RG_X = 4 * 128, RG_B = 4 * 128, RG_W = (2 * KP / 8) * 128;
+  static constexpr uint32_t O_X = 0, O_W = O_X + 16 * RG_X, O_B = O_W + 16 * RG_W, O_MISC = O_B + (KP / 8) * RG_B;
+  static constexpr uint32_t TOTAL = O_MISC + 64;
+  static constexpr uint32_t TMEM_COLS = (KP + 16) <= 32 ? 32 : ((KP + 16) <= 64 ? 64 : 128);
+};
+
+#ifndef PDEIP_ITC8_MINB
+#define PDEIP_ITC8_MINB 8
+#endif
+template <int KP, bool BLK, int MINB>
+__global__ void __launch_bounds__(128, MINB) kl_integrate_tc8_kernel(const IntegrateArgs a, int* status) {
+  using S = Cfg8<KP>;
+  constexpr int DP = 8;
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(sm + S::O_MISC);
+  uint32_t* tmem_p = reinterpret_cast<uint32_t*>(sm + S::O_MISC + 8);
+  volatile int* dead_p = reinterpret_cast<volatile int*>(sm + S::O_MISC + 12);
+
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_p), S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(mbar_p), 1);
+    fence_mbar_init();
+    *dead_p = 0;
+  }
+  const float cs = a.inv_sigma2 * 1.4426950408889634f;
+  if (tid < KP) {  // B tile row of centre tid
+    float hi_f[8], lo_f[8], s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float w = (tid < a.n_gaussian) ? cs * a.drift_params[tid * DP + c] : 0.f;
+      hi_f[c] = __bfloat162float(__float2bfloat16_rn(w));
+      lo_f[c] = __bfloat162float(__float2bfloat16_rn(w - hi_f[c]));
+      const float m = hi_f[c] + lo_f[c];
+      s2 = fmaf(m, m, s2);
+    }
+    const float b = (tid < a.n_gaussian) ? -0.5f * s2 / cs : -1.0e30f;  // padding centres: weight exactly 0
+    const float b0 = __bfloat162float(__float2bfloat16_rn(b));
+    const float b1 = __bfloat162float(__float2bfloat16_rn(b - b0));
+    const float b2 = __bfloat162float(__float2bfloat16_rn(b - b0 - b1));
+    const float bias[8] = {b0, b1, b2, 0.f, 0.f, 0.f, 0.f, 0.f};
+    store_chunk(sm + S::O_B, chunk_off(tid, 0, S::RG_B), hi_f);
+    store_chunk(sm + S::O_B, chunk_off(tid, 1, S::RG_B), hi_f);
+    store_chunk(sm + S::O_B, chunk_off(tid, 2, S::RG_B), lo_f);
+    store_chunk(sm + S::O_B, chunk_off(tid, 3, S::RG_B), bias);
+  }
+  *reinterpret_cast<uint4*>(sm + S::O_X + chunk_off(tid, 3, S::RG_X)) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_p;
+  const uint32_t t_row = tbase + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_logit = t_row, t_acc = t_row + KP;
+  const uint32_t mbar = smem_u32(mbar_p);
+  const uint32_t sX = smem_u32(sm + S::O_X), sW = smem_u32(sm + S::O_W), sB = smem_u32(sm + S::O_B);
+  uint8_t* const rowX = sm + S::O_X + (uint32_t)(tid & 7) * 16u + (uint32_t)(tid >> 3) * S::RG_X;
+  uint8_t* const rowW = sm + S::O_W + (uint32_t)(tid & 7) * 16u + (uint32_t)(tid >> 3) * S::RG_W;
+  uint32_t phase = 0;
+
+  const int64_t n_raw = (int64_t)blockIdx.x * 128 + tid;
+  const int64_t n = n_raw < a.n ? n_raw : a.n - 1;  // ragged last tile: repeat the last particle (see above)
+  const uint64_t pid = a.particle_offset + (uint64_t)n;
+  float2 q[4], p[4];
+  {
+    const float4* z4 = reinterpret_cast<const float4*>(a.z0 + n * 16);
+    const float4 q0 = z4[0], q1 = z4[1], p0 = z4[2], p1 = z4[3];
+    q[0] = make_float2(q0.x, q0.y); q[1] = make_float2(q0.z, q0.w); q[2] = make_float2(q1.x, q1.y); q[3] = make_float2(q1.z, q1.w);
+    p[0] = make_float2(p0.x, p0.y); p[1] = make_float2(p0.z, p0.w); p[2] = make_float2(p1.x, p1.y); p[3] = make_float2(p1.z, p1.w);
+  }
+  const float t0 = philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
+  const int Sn = a.n_steps;
+  const int64_t plane = BLK ? 128 : (int64_t)Sn * a.n;
+  const int64_t sstride = BLK ? (int64_t)gridDim.x * (3 * DP * 128) : a.n;
+  float* o = BLK ? a.traj + ((int64_t)blockIdx.x * (3 * DP) * 128 + tid) : a.traj + n;
+  const float rcs = 1.0f / cs;
+
+  auto wait_commit = [&]() {
+    if (!*dead_p) {
+      if (!mbar_wait(mbar, phase, 1u << 22)) {
+        *dead_p = 1;
+        atomicExch(status, 2);
+      }
+    }
+    phase ^= 1u;
+    fence_after_sync();
+  };
+  auto kick = [&](int s, float dmp, float sq, int j) {  // p <- p (1 - gamma h) + sqrt(2h) xi, coordinates 4j .. 4j+3
+    const float2 dmp2 = make_float2(dmp, dmp), sq2 = make_float2(sq, sq);
+    float r4[4];
+    philox_normal4_rk(a.rk, pid, a.step_offset + (uint32_t)s, (uint32_t)j, r4);
+    p[2 * j] = __ffma2_rn(sq2, make_float2(r4[0], r4[1]), __fmul2_rn(p[2 * j], dmp2));
+    p[2 * j + 1] = __ffma2_rn(sq2, make_float2(r4[2], r4[3]), __fmul2_rn(p[2 * j + 1], dmp2));
+  };
+
+#pragma unroll 1
+  for (int s = 0; s <= Sn; ++s) {
+    const float h = (s == 0) ? t0 : ((s == Sn) ? a.dt - t0 : a.dt);  // sampling_utils.py:33,45-46
+    const float sq = sqrtf(h) * 1.41421356237309515f;
+    const float dmp = 1.f - a.gamma * h;
+    {
+      uint4 hi, lo;
+      split2(q[0], hi.x, lo.x);
+      split2(q[1], hi.y, lo.y);
+      split2(q[2], hi.z, lo.z);
+      split2(q[3], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(rowX) = hi;
+      *reinterpret_cast<uint4*>(rowX + 128) = lo;
+      *reinterpret_cast<uint4*>(rowX + 256) = hi;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == ((2 * s) & 3) && elect_one()) {
+      fence_after_sync();
+      gemm_kk(tbase, sX, S::RG_X, 0, sB, S::RG_B, 0, 32, KP, 0u);
+      commit(mbar);
+    }
+    __syncwarp();
+    kick(s, dmp, sq, 0);
+    wait_commit();
+
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < KP / 16; ++c) {
+      float l[16];
+      tm_ld16(t_logit + 16 * c, l);
+      tm_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m = fmaxf(m, l[i]);
+    }
+    float2 se2 = make_float2(0.f, 0.f);
+    {
+      const float2 nm2 = make_float2(-m, -m);
+#pragma unroll
+      for (int c = 0; c < KP / 16; ++c) {
+        float l[16];
+        tm_ld16(t_logit + 16 * c, l);
+        tm_wait_ld();
+        float2 e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 t = __fadd2_rn(make_float2(l[2 * i], l[2 * i + 1]), nm2);
+          e[i] = make_float2(ex2f(t.x), ex2f(t.y));
+          se2 = __fadd2_rn(se2, e[i]);
+        }
+#pragma unroll
+        for (int hcg = 0; hcg < 2; ++hcg) {
+          uint4 hi, lo;
+          split2(e[4 * hcg], hi.x, lo.x);
+          split2(e[4 * hcg + 1], hi.y, lo.y);
+          split2(e[4 * hcg + 2], hi.z, lo.z);
+          split2(e[4 * hcg + 3], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(rowW + (2 * c + hcg) * 128) = hi;
+          *reinterpret_cast<uint4*>(rowW + (KP / 8 + 2 * c + hcg) * 128) = lo;
+        }
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == ((2 * s + 1) & 3) && elect_one()) {
+      fence_after_sync();
+      gemm_km(tbase + KP, sW, S::RG_W, 0, sB, S::RG_B, 0, 0, KP, 16, 0u);    // e_hi . [mu_hi | mu_hi]
+      gemm_km(tbase + KP, sW, S::RG_W, KP, sB, S::RG_B, 0, 0, KP, 16, 1u);   // e_lo . [mu_hi | mu_hi]
+      gemm_km(tbase + KP, sW, S::RG_W, 0, sB, S::RG_B, 16, 0, KP, 16, 1u);   // e_hi . [mu_lo | bias]
+      commit(mbar);
+    }
+    __syncwarp();
+    kick(s, dmp, sq, 1);
+    wait_commit();
+
+    const float rn = -rcs / (se2.x + se2.y);
+    const float2 rn2 = make_float2(rn, rn), is2 = make_float2(a.inv_sigma2, a.inv_sigma2);
+    const float2 nh2 = make_float2(-h, -h), h2 = make_float2(h, h);
+    float* og = (s == 0 ? o : o - sstride) + 2 * DP * plane;
+    float acc[8];
+    tmem_ld8(t_acc, acc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 g = __fmul2_rn(__ffma2_rn(make_float2(acc[2 * k], acc[2 * k + 1]), rn2, q[k]), is2);
+      __stcs(og + (2 * k) * plane, g.x);
+      __stcs(og + (2 * k + 1) * plane, g.y);
+      p[k] = __ffma2_rn(nh2, g, p[k]);
+      q[k] = __ffma2_rn(h2, p[k], q[k]);
+    }
+    if (s < Sn) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __stcs(o + (2 * i) * plane, q[i].x);
+        __stcs(o + (2 * i + 1) * plane, q[i].y);
+        __stcs(o + (DP + 2 * i) * plane, p[i].x);
+        __stcs(o + (DP + 2 * i + 1) * plane, p[i].y);
+      }
+    }
+    o += sstride;
+  }
+  {
+    float4* zl = reinterpret_cast<float4*>(a.z_last + n * 16);
+    zl[0] = make_float4(q[0].x, q[0].y, q[1].x, q[1].y);
+    zl[1] = make_float4(q[2].x, q[2].y, q[3].x, q[3].y);
+    zl[2] = make_float4(p[0].x, p[0].y, p[1].x, p[1].y);
+    zl[3] = make_float4(p[2].x, p[2].y, p[3].x, p[3].y);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, S::TMEM_COLS);
+}
+
+template <int KP>
+static int launch8(const IntegrateArgs& a, int* status, cudaStream_t st) {
+  using S = Cfg8<KP>;
+  const int64_t grid = (a.n + 127) / 128;
+  const char* mb = getenv("PDEIP_ITC8_MINB");  // tuning knob: CTAs per SM the register budget is sized for
+  const bool eight = mb ? (mb[0] == '8') : (PDEIP_ITC8_MINB == 8);
+  void (*kern)(const IntegrateArgs, int*);
+  if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
+    kern = eight ? kl_integrate_tc8_kernel<KP, true, 8> : kl_integrate_tc8_kernel<KP, true, 6>;
+  else
+    kern = eight ? kl_integrate_tc8_kernel<KP, false, 8> : kl_integrate_tc8_kernel<KP, false, 6>;
+  PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+  kern<<<(unsigned)grid, 128, S::TOTAL, st>>>(a, status);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
 template <int DP, int KP>
 static int launch(const IntegrateArgs& a, int* status, cudaStream_t st) {
   using S = Cfg<DP, KP>;
@@ -375,9 +614,9 @@ static int launch(const IntegrateArgs& a, int* status, cudaStream_t st) {
 }  // namespace itc
 
 // true if the call is served by the tensor-core kernel: the production configuration of kl_integrate_fast_kernel
-// (checked by the caller) with the GMM drift, d = 16 or 32 and at most 64 centres
+// (checked by the caller) with the GMM drift, d = 8, 16 or 32 and at most 64 centres
 bool integrate_tensor_ok(const IntegrateArgs& a, int drift_kind) {
-  return drift_kind == PDEIP_DRIFT_GMM && (a.d == 16 || a.d == 32) && a.n_gaussian >= 1 && a.n_gaussian <= 64 &&
+  return drift_kind == PDEIP_DRIFT_GMM && (a.d == 8 || a.d == 16 || a.d == 32) && a.n_gaussian >= 1 && a.n_gaussian <= 64 &&
          getenv("PDEIP_NO_TC_INTEGRATOR") == nullptr;
 }
 
@@ -385,6 +624,12 @@ int launch_integrate_tensor(const IntegrateArgs& a, cudaStream_t st) {
   int* status = tensor_status_word();
   PDEIP_REQUIRE(status != nullptr, PDEIP_ERR_CUDA, "cannot allocate the tensor-path status word");
   const int kp = (a.n_gaussian + 15) / 16 * 16;
+  if (a.d == 8) {
+    if (kp == 16) return itc::launch8<16>(a, status, st);
+    if (kp == 32) return itc::launch8<32>(a, status, st);
+    if (kp == 48) return itc::launch8<48>(a, status, st);
+    return itc::launch8<64>(a, status, st);
+  }
   if (a.d == 32) {
     if (kp == 16) return itc::launch<32, 16>(a, status, st);
     if (kp == 32) return itc::launch<32, 32>(a, status, st);

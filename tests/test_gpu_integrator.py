@@ -288,7 +288,8 @@ def unblock(tr):
 
 @pytest.mark.parametrize("d,K,n,S", [(32, 64, 4096 + 37, 12), (32, 64, 300, 200), (32, 40, 1000, 12), (32, 7, 129, 12),
                                      (16, 16, 1000, 12), (16, 64, 2048, 12), (16, 33, 515, 50), (32, 64, 4096, 12),
-                                     (16, 48, 640, 30)])
+                                     (16, 48, 640, 30), (8, 16, 4096, 12), (8, 16, 1000, 200), (8, 3, 130, 12),
+                                     (8, 40, 640, 30), (8, 64, 256, 12)])
 def test_tensor_core_gmm_integrator_matches_fp32_kernel(cuda, d, K, n, S):
     """pdeip_kl_integrate_path(PDEIP_PATH_TENSOR): particle x centre contraction and softmax-weighted centre sum on
     tcgen05 with bf16 hi + lo split operands, against the fp32 production kernel on the same Philox stream.
