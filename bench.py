@@ -277,7 +277,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and shard.world == 1:
             line["cpu_baseline"] = cpu_baseline(w, seconds_hint=15.0)
-        print(json.dumps(line))
+        emit_result(line)
     if shard.world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -355,11 +355,27 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_result(line)
+
+
+_RESULT_OUT = None
+
+
+def emit_result(line: dict) -> None:
+    """The ONE JSON line of the run, on the process's original stdout."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's debug output (the version banner at NCCL_DEBUG >= VERSION) goes to stderr
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner from C with
+    # NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says at 8 ranks), so file descriptor 1 is pointed at stderr for the
+    # whole run and the result goes to a private duplicate of the original stdout.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
