@@ -12,7 +12,8 @@ import re
 from typing import Dict, List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdeip.so")
+# PDEIP_LIB: an instrumented build of the same library (tools/tensor_phase_trace.py); the product path has no other source
+LIB_PATH = os.environ.get("PDEIP_LIB") or os.path.join(_HERE, "libpdeip.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pdeip.h")
 
 
