@@ -368,6 +368,16 @@ __device__ __noinline__ void true_grad_chunk(const ResidualArgs& a, const float*
 }
 __device__ __forceinline__ float unp(const uint32_t* r, int i) { return (i & 1) ? bf_hi(r[i >> 1]) : bf_lo(r[i >> 1]); }
 
+// ---- packed fp32x2 epilogue arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot per two values).  Every array of
+// the epilogues is paired (2 i, 2 i + 1): adjacent TMEM columns, the two halves of a packed bf16 word. -------------
+#ifndef PDEIP_TC_PACKED
+#define PDEIP_TC_PACKED 1
+#endif
+__device__ __forceinline__ float2 pr(const float* v, int i) { return make_float2(v[2 * i], v[2 * i + 1]); }
+__device__ __forceinline__ void st2(float* v, int i, float2 x) { v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+__device__ __forceinline__ float2 unp2(const uint32_t* r, int i) { return make_float2(bf_lo(r[i]), bf_hi(r[i])); }
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
 template <int DP, int NS>
 __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
   using S = Cfg<DP, NS>;
@@ -713,6 +723,19 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(bias_s + (l1 ? 0 : 32) + u16 + 4 * i);
         tm_wait_ld();
         float t[16], s1[16], q1[16], q2[16];
+#if PDEIP_TC_PACKED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 zb = __fadd2_rn(pr(z0, i), pr(bb, i));
+          const float2 t2 = make_float2(tanh_fast(zb.x), tanh_fast(zb.y));
+          const float2 s2 = __ffma2_rn(__fmul2_rn(t2, bc2(-1.f)), t2, bc2(1.f));
+          const float2 z12 = pr(z1, i);
+          const float2 q = __fmul2_rn(s2, z12);
+          float2 r = __fmul2_rn(__fmul2_rn(t2, q), z12);
+          if constexpr (!l1) r = __ffma2_rn(s2, pr(z2, i), r);
+          st2(t, i, t2); st2(s1, i, s2); st2(q1, i, q); st2(q2, i, r);
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           t[i] = tanh_fast(z0[i] + bb[i]);
@@ -721,6 +744,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           const float w = t[i] * q1[i];
           q2[i] = l1 ? w * z1[i] : fmaf(s1[i], z2[i], w * z1[i]);
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           put_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
@@ -745,6 +769,24 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const float k8 = 8.f * mk, kg = gamma4 * mk;
         float d1 = 0.f, d2a = 0.f, d2b = 0.f;
         float za[24], sv[24], sp[24];
+#if PDEIP_TC_PACKED
+        {
+          float2 e1 = bc2(0.f), e2a = bc2(0.f), e2b = bc2(0.f);
+          const float2 k82 = bc2(k8), nk82 = bc2(-k8), kg2 = bc2(kg);
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const float2 uu = __fadd2_rn(pr(u, i), pr(bb, i));
+            const float2 v1 = pr(u1, i), v2 = pr(u2, i);
+            e1 = __ffma2_rn(uu, v1, e1);
+            e2a = __ffma2_rn(v1, v1, e2a);
+            e2b = __ffma2_rn(uu, v2, e2b);
+            st2(za, i, __fmul2_rn(k82, uu));
+            st2(sv, i, __ffma2_rn(nk82, v1, __fmul2_rn(kg2, uu)));
+            st2(sp, i, __ffma2_rn(k82, v2, __fmul2_rn(kg2, v1)));
+          }
+          d1 = e1.x + e1.y; d2a = e2a.x + e2a.y; d2b = e2b.x + e2b.y;
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
           const float uu = u[i] + bb[i];
@@ -755,6 +797,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           sv[i] = fmaf(-k8, u1[i], kg * uu);
           sp[i] = fmaf(k8, u2[i], kg * u1[i]);
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           put_chunk(Z, (ZC_ZA2 + 3 * half + c) * 128, za + 8 * c);
@@ -787,6 +830,17 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         tm_wait_ld();
         TC_FINE(0);
         float za[16], zb[16], pz[16];
+#if PDEIP_TC_PACKED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 s2 = unp2(s1p, i), aa2 = pr(aa, i), a12 = pr(a1, i), ab2 = pr(ab1, i);
+          const float2 tt = __fmul2_rn(pr(t, i), bc2(2.f));
+          const float2 qq = __fmul2_rn(aa2, a12);
+          st2(za, i, __fmul2_rn(aa2, s2));
+          st2(zb, i, __ffma2_rn(tt, qq, __fmul2_rn(s2, ab2)));
+          st2(pz, i, __fmul2_rn(a12, __ffma2_rn(__fmul2_rn(tt, bc2(-1.f)), ab2, qq)));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float s1 = unp(s1p, i);
@@ -795,6 +849,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           zb[i] = fmaf(2.f * t[i], qq, s1 * ab1[i]);
           pz[i] = a1[i] * fmaf(-2.f * t[i], ab1[i], qq);
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           put_chunk(Z, ((l2 ? ZC_ZA1 : ZC_ZA0) + 2 * half + c) * 128, za + 8 * c);
@@ -860,11 +915,20 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         tm_ldf<16>(LA + (l1 ? C_ZG0 : C_ZG1) + u16, zg);
         tm_wait_ld();
         float ag[16], cc[16];
+#if PDEIP_TC_PACKED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 g2 = __fmul2_rn(unp2(s1p, i), pr(zg, i));
+          st2(ag, i, g2);
+          st2(cc, i, __fadd2_rn(pr(a2, i), g2));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           ag[i] = unp(s1p, i) * zg[i];
           cc[i] = a2[i] + ag[i];
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           put_chunk(At, (AC_A1 + 2 * half + c) * 128, ag + 8 * c);
@@ -880,11 +944,20 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         if constexpr (kEarlyLoads) wait_gemm();
         tm_ldf<24>(LA + C_UG + u24, ug);
         tm_wait_ld();
+#if PDEIP_TC_PACKED
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const float2 v = __ffma2_rn(bc2(8.f), pr(ug, i), unp2(spp, i));
+          st2(s0, i, v);
+          st2(db2, i, __fadd2_rn(pr(db2, i), v));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
           s0[i] = fmaf(8.f, ug[i], unp(spp, i));
           db2[i] += s0[i];
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 3; ++c) put_chunk(Z, (ZC_TA + 3 * half + c) * 128, s0 + 8 * c);
         TC_PROBE(18, u24, s0, 24);
@@ -911,6 +984,17 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         tm_ldf<16>(LA + (l2 ? C_AA2R : C_AA1R) + u16, aa);
         tm_wait_ld();
         float zb[16];
+#if PDEIP_TC_PACKED
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 m0 = __ffma2_rn(unp2(s1p, i), pr(ab, i), unp2(pzp, i));
+          const float2 ta = __fmul2_rn(__fmul2_rn(pr(t, i), bc2(-2.f)), pr(aa, i));
+          const float2 v = __ffma2_rn(ta, pr(cc, i), m0);
+          st2(zb, i, v);
+          if (l2) st2(db1, i, __fadd2_rn(pr(db1, i), v));
+          else st2(db0, i, __fadd2_rn(pr(db0, i), v));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float m0 = fmaf(unp(s1p, i), ab[i], unp(pzp, i));
@@ -918,6 +1002,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           if (l2) db1[i] += zb[i];
           else db0[i] += zb[i];
         }
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
         TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
