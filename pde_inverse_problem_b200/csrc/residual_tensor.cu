@@ -638,8 +638,27 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       if (NS == 2 && s == 1) load_into(xin1, t);
       else load_into(xin0, t);
     };
+#ifndef PDEIP_TC_L2_PREFETCH
+#define PDEIP_TC_L2_PREFETCH 1
+#endif
+    // Input staging.  A register prefetch issued one tile ahead (in E10) shares a scoreboard with the phase's own
+    // LDS / TMEM loads, so the first wait after it sits out the full DRAM latency (~1.4 k cycles per slot and tile in the
+    // phase trace).  Instead E10 only pulls the next tile's lines into L2 (prefetch.global.L2: no destination, nothing
+    // to wait for) and E0 issues the loads itself, before its commit wait: they hit L2 and land behind that wait.
+    auto prefetch_inputs = [&](int64_t t) {
+      if (t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // ragged last tile: not worth a special case
+      const int n_lines = dimw * 4;  // 128 points x dimw floats = dimw * 4 lines of 128 B
+      for (int l = row + 128 * half; l < n_lines; l += kEpiThreads) {
+        const float* addr;
+        if (a.layout == PDEIP_LAYOUT_SOA) addr = a.points + (int64_t)(l >> 2) * a.n_points + t * 128 + (l & 3) * 32;
+        else addr = a.points + t * 128 * dimw + (int64_t)l * 32;  // AOS and BLOCK128: the tile is one contiguous block
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+      }
+    };
+#if !PDEIP_TC_L2_PREFETCH
     load_inputs(0, (int64_t)blockIdx.x * NS);
     if constexpr (NS == 2) load_inputs(1, (int64_t)blockIdx.x * NS + 1);
+#endif
 
     bool first = true;
     int64_t base = (int64_t)blockIdx.x * NS;
@@ -682,6 +701,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         TC_TRACE(1);
       };
       constexpr bool kEarlyLoads = DP <= 16;  // at d = 32 the values held across the wait cost more in spills than they hide
+#if PDEIP_TC_L2_PREFETCH
+      if constexpr (ph == 0) load_inputs(s, tile);
+#endif
       if constexpr (ph <= 3 || ph == 6 || !kEarlyLoads) wait_gemm();
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
         auto emit = [&](const float (&xin)[NI][8]) {
@@ -967,7 +989,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // next tile of this slot: issue the input loads first, so that the DRAM latency overlaps this phase's work (the
         // proxy fence of epi_arrive waits for every outstanding load of the thread: a load issued late in a phase is a
         // blocking load)
+#if PDEIP_TC_L2_PREFETCH
+        if constexpr (l2) prefetch_inputs(tile + tile_stride);
+#else
         if constexpr (l2) load_inputs(s, tile + tile_stride);
+#endif
         const uint8_t* At = l2 ? A2 : A1;
         float ab[16], aa[16], t[16], cc[16];
         uint32_t s1p[8], pzp[8];
