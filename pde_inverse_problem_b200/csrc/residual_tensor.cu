@@ -395,8 +395,14 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   uint64_t* mbar_p = reinterpret_cast<uint64_t*>(sm + S::O_MISC);  // [slot]
   uint32_t* tmem_p = reinterpret_cast<uint32_t*>(sm + S::O_MISC + 64);
 
-  const int64_t n_tiles = (a.n_points + 127) / 128;
-  if ((int64_t)blockIdx.x * NS >= n_tiles) return;  // nothing to do for this CTA (uniform)
+  // Every CTA owns a CONTIGUOUS range of tiles (a multiple of NS): its input stream walks one region of the point set
+  // front to back (one new 2 MB page every ~170 tiles at d = 8 instead of every tile with a grid-strided assignment).
+  // n_tiles is the END of this CTA's range.
+  const int64_t n_tiles_all = (a.n_points + 127) / 128;
+  const int64_t per_cta = ((n_tiles_all + gridDim.x - 1) / gridDim.x + NS - 1) / NS * NS;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
+  if (tile_begin >= n_tiles_all) return;  // nothing to do for this CTA (uniform)
+  const int64_t n_tiles = tile_begin + per_cta < n_tiles_all ? tile_begin + per_cta : n_tiles_all;
 
   // ---- one-time set-up: TMEM, mbarriers, zeroed operand tiles, split weights in core-matrix layout ------------
   if (warp == 0) {
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   fence_after_sync();
 
   const uint32_t TB = *tmem_p;
-  const int64_t tile_stride = (int64_t)gridDim.x * NS;
+  const int64_t tile_stride = NS;
 
   // ==========================================================================================================
   // MMA warp: one lane issues every tcgen05.mma, phase by phase, slot by slot
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
     // the result is below 1e-3 (tests/tensor_v2_model.py study), the forward and input-gradient GEMMs keep hi + lo.
 #pragma unroll 1
-    for (int64_t base = (int64_t)blockIdx.x * NS; base < n_tiles; base += tile_stride) {
+    for (int64_t base = tile_begin; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
       for (int ph = 0; ph < 12; ++ph) {
 #pragma unroll 1
@@ -643,25 +649,29 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
     // Input staging.  A register prefetch issued one tile ahead (in E10) shares a scoreboard with the phase's own
     // LDS / TMEM loads, so the first wait after it sits out the full DRAM latency (~1.4 k cycles per slot and tile in the
-    // phase trace).  Instead E10 only pulls the next tile's lines into L2 (prefetch.global.L2: no destination, nothing
-    // to wait for) and E0 issues the loads itself, before its commit wait: they hit L2 and land behind that wait.
+    // phase trace).  Instead E10 only asks the TMA unit to pull the next tile into L2 (cp.async.bulk.prefetch.L2: no
+    // destination register, nothing to wait for; prefetch.global.L2 = CCTL.PF2 measured ~700 cycles per phase) and E0
+    // issues the loads itself, before its commit wait: they hit L2 and land behind that wait.
     auto prefetch_inputs = [&](int64_t t) {
       if (t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // ragged last tile: not worth a special case
-      const int n_lines = dimw * 4;  // 128 points x dimw floats = dimw * 4 lines of 128 B
-      for (int l = row + 128 * half; l < n_lines; l += kEpiThreads) {
-        const float* addr;
-        if (a.layout == PDEIP_LAYOUT_SOA) addr = a.points + (int64_t)(l >> 2) * a.n_points + t * 128 + (l & 3) * 32;
-        else addr = a.points + t * 128 * dimw + (int64_t)l * 32;  // AOS and BLOCK128: the tile is one contiguous block
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+      if (a.layout == PDEIP_LAYOUT_SOA) {  // dimw component segments of 512 B
+        if ((a.n_points & 3) == 0 && half == 0 && row < dimw)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.points + (int64_t)row * a.n_points + t * 128),
+                       "r"(512u)
+                       : "memory");
+      } else if (half == 0 && row == 0) {  // AOS and BLOCK128: the tile is one contiguous block of 128 x dimw floats
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.points + t * 128 * dimw),
+                     "r"((uint32_t)(512 * dimw))
+                     : "memory");
       }
     };
 #if !PDEIP_TC_L2_PREFETCH
-    load_inputs(0, (int64_t)blockIdx.x * NS);
-    if constexpr (NS == 2) load_inputs(1, (int64_t)blockIdx.x * NS + 1);
+    load_inputs(0, tile_begin);
+    if constexpr (NS == 2) load_inputs(1, tile_begin + 1);
 #endif
 
     bool first = true;
-    int64_t base = (int64_t)blockIdx.x * NS;
+    int64_t base = tile_begin;
 
     // one epilogue phase of one slot: wait for the previous GEMM phase of that slot, compute, signal the MMA warp
     // The phase bodies are shared by the two slots (runtime slot offsets): E_k(slot 0) and E_k(slot 1) run back to
