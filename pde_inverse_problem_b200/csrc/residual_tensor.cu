@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
         TC_TRACE(1);
       };
-      constexpr bool kEarlyLoads = DP <= 16;  // at d = 32 the values held across the wait cost more in spills than they hide
+      constexpr bool kEarlyLoads = true;  // (at d = 32 this used to spill; the shorter life of the input registers fixed that)
 #if PDEIP_TC_L2_PREFETCH
       if constexpr (ph == 0) load_inputs(s, tile);
 #endif
