@@ -234,11 +234,11 @@ def run_ours(args):
         res_rate = n * hp.s_emit / t_res  # per GPU
         res_tflops = res_rate * flop_eval / 1e12
         # DRAM bytes per residual launch: ncu --set full of this kernel (profiles/r01_summary_tc_integrator.md) measured
-        # 96.5 B per point at d = 8 (96 B algorithmic: x, v, grad U): scaled to this run's points per launch
+        # 96.6 B per point at d = 8 (96 B algorithmic: x, v, grad U): scaled to this run's points per launch
         pts_launch = cfg.chunk * hp.s_emit
         if path == L.PATH_TENSOR and d == 8:
-            res_traffic = 96.5 * pts_launch
-            res_traffic_src = "ncu dram__bytes_read+write per point (151 552-particle capture: 2.925 GB for 30.3 M points) x points per launch"
+            res_traffic = 96.6 * pts_launch
+            res_traffic_src = "ncu dram__bytes_read+write per point (151 552-particle capture: 2.927 GB for 30.3 M points) x points per launch"
         else:
             res_traffic, res_traffic_src = None, "not captured for this configuration"
         int_rate = n * (S + 1) / t_int
