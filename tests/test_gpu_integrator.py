@@ -361,3 +361,28 @@ def test_block128_trajectory_layout(cuda, drift, d, K):
         assert torch.equal(unblock(tr_b), tr_s) and torch.equal(zl_b, zl_s)
     with pytest.raises(Exception):
         run(L.TRAJ_BLOCK128, nn=n - 1)
+
+
+@pytest.mark.parametrize("d,K,n,layout_name", [(32, 64, 300, "soa"), (32, 64, 384, "block"), (8, 16, 1000, "soa"),
+                                               (8, 16, 1024, "block"), (16, 20, 129, "soa")])
+def test_tensor_core_integrator_writes_stay_in_bounds(cuda, d, K, n, layout_name):
+    """Guard bands around the trajectory and final-state buffers (compute-sanitizer is not available on the pool):
+    the tcgen05 integrator, ragged last tile included, writes every element of its outputs and nothing else."""
+    from pde_inverse_problem_b200 import ops, _lib as L
+    S, pad = 7, 4096
+    layout = L.TRAJ_BLOCK128 if layout_name == "block" else L.TRAJ_TIME_SOA
+    g = torch.Generator().manual_seed(1)
+    z0 = torch.randn(n, 2 * d, generator=g).to(cuda)
+    mus = (torch.rand(K, d, generator=g) * 8 - 4).to(cuda)
+    need = 3 * d * S * n
+    sentinel = float("nan")
+    tbuf = torch.full((need + 2 * pad,), sentinel, device=cuda)
+    zbuf = torch.full((2 * d * n + 2 * pad,), sentinel, device=cuda)
+    zl, tr, _ = ops.kl_integrate(z0, S, 0.01, 0.5, L.DRIFT_GMM, mus, n_gaussian=K, seed=3, traj_layout=layout,
+                                 emit_drift=True, path=L.PATH_TENSOR, traj_out=tbuf[pad:pad + need],
+                                 z_last_out=zbuf[pad:pad + 2 * d * n].view(n, 2 * d))
+    torch.cuda.synchronize()
+    assert ops.tensor_path_status() == 0
+    assert torch.isnan(tbuf[:pad]).all() and torch.isnan(tbuf[pad + need:]).all()
+    assert torch.isnan(zbuf[:pad]).all() and torch.isnan(zbuf[pad + 2 * d * n:]).all()
+    assert torch.isfinite(tr).all() and torch.isfinite(zl).all()
