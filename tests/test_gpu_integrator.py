@@ -386,3 +386,30 @@ def test_tensor_core_integrator_writes_stay_in_bounds(cuda, d, K, n, layout_name
     assert torch.isnan(tbuf[:pad]).all() and torch.isnan(tbuf[pad + need:]).all()
     assert torch.isnan(zbuf[:pad]).all() and torch.isnan(zbuf[pad + 2 * d * n:]).all()
     assert torch.isfinite(tr).all() and torch.isfinite(zl).all()
+
+
+@pytest.mark.parametrize("d,K,n,S", [(8, 16, 256, 40), (32, 64, 256, 40), (16, 20, 384, 25)])
+def test_tensor_core_integrator_matches_float64_oracle(cuda, d, K, n, S):
+    """The production integrator (GMM drift on tcgen05, in-register Philox noise, BLOCK128 trajectory with grad U)
+    against the float64 restatement of utils/sampling_utils.py:6-52 + core/potential.py:32-61, fed with the same Philox
+    draws (pdeip_philox_normals / _uniforms).  Tolerance class "bf16 GEMM paths" (1e-2); asserted at 2e-3."""
+    from pde_inverse_problem_b200 import ops, _lib as L
+    T, gamma, seed, off = 0.01 * S, 0.5, 77, 4242
+    dt = T / S
+    g = torch.Generator().manual_seed(d + K)
+    z0 = torch.randn(n, 2 * d, generator=g, dtype=torch.float64) * torch.cat([torch.full((d,), 2.0), torch.full((d,), 0.3)]).double()
+    mus = torch.rand(K, d, generator=g, dtype=torch.float64) * 8 - 4
+    noise = ops.philox_normals(n, S + 1, d, seed=seed, particle_offset=off, device=cuda).double().cpu()
+    tau0 = ops.philox_uniforms(n, seed=seed, particle_offset=off, device=cuda).float().mul(dt).double().cpu()
+    last, traj, _ = o_int.underdamped_langevin_dynamics_scan(z0.float().double(), S, dt, noise, tau0,
+                                                             o_pot.GMMPotential(mus.float().double(), 1.0).gradient, gamma)
+    zl, tr, _ = ops.kl_integrate(z0.float().to(cuda), S, dt, gamma, L.DRIFT_GMM, mus.float().to(cuda), n_gaussian=K,
+                                 seed=seed, particle_offset=off, traj_layout=L.TRAJ_BLOCK128, emit_drift=True,
+                                 path=L.PATH_TENSOR)
+    torch.cuda.synchronize()
+    assert ops.tensor_path_status() == 0
+    got = tr.permute(1, 3, 0, 2).reshape(n, S, 3 * d)
+    assert relmax(got[..., : 2 * d], traj) < 2e-3
+    assert relmax(zl, last) < 2e-3
+    gref = o_pot.vg_gmm_V(traj[..., :d].reshape(-1, d), mus.float().double(), 1.0).reshape(n, S, d)
+    assert relmax(got[..., 2 * d:], gref) < 2e-3
