@@ -1,9 +1,10 @@
 // integrator_tc.cu — K1 with the GMM drift on the tensor cores (PDEIP_PATH_TENSOR of pdeip_kl_integrate_path).
 //
-// Replaces utils/sampling_utils.py:6-52 with potential_grad = GMMPotential.gradient (core/potential.py:32-61) for the
-// large shapes (C5: d = 32, K = 64), where the particle x centre distance contraction (4 K d FLOP per particle-step)
-// is what bounds the CUDA-core kernel.  One CTA = 128 particles = one 128-row tcgen05 tile, thread = particle = TMEM
-// lane; (q, p) stay in registers for all S + 1 steps.  Per step:
+// Replaces utils/sampling_utils.py:6-52 with potential_grad = GMMPotential.gradient (core/potential.py:32-61): the
+// particle x centre distance contraction (4 K d FLOP per particle-step) is what bounds the CUDA-core kernel (22 % of
+// the HBM roofline at C5: d = 32, K = 64; 56 % at C3: d = 8, K = 16).  One CTA = 128 particles = one 128-row tcgen05
+// tile, thread = particle = TMEM lane; (q, p) stay in registers for all S + 1 steps.  Per step (d = 16, 32; the d = 8
+// kernel further down packs the same operands into full K = 16 steps):
 //
 //   GEMM 1   L[128 x K]  = [1 | x_hi | x_lo | x_hi] . [b ; mu~_hi ; mu~_hi ; mu~_lo]^T       (tcgen05.mma, bf16 -> fp32)
 //            mu~ = mu log2(e) / sigma^2,  b_k = -|mu~_k|^2 / (2 log2(e) / sigma^2)  (three bf16 terms through a ones column)
@@ -16,7 +17,9 @@
 // the result equals the fp32 closed form evaluated at inputs perturbed by < 1e-5 relative (tests: 2e-3 on whole
 // trajectories against the fp32 kernel; tolerance class "bf16 GEMM paths" = 1e-2).  The Philox noise of a step does
 // not depend on the drift, so it is generated while the step's GEMMs are in flight.  Same Philox stream, tau0, step
-// schedule and [3d][S][N] output as kl_integrate_fast_kernel (integrator.cu).
+// schedule and outputs ([S][N/128][3d][128] or [3d][S][N] trajectory with grad U, final state) as
+// kl_integrate_fast_kernel (integrator.cu).  Measured: 70.8 % (d = 32, K = 64) and 69 % (d = 8, K = 16) of the HBM copy
+// bandwidth; bound by instruction issue and MUFU together (profiles/r01_summary_tc_integrator.md).
 #include "common.cuh"
 #include "integrator_args.cuh"
 #include "philox.cuh"
