@@ -20,6 +20,26 @@ from . import ops, parallel
 from .core.optimizer import AdamL2, OptState
 
 
+def integrator_wave(d: int, drift_kind: int, n_gaussian: int, path: int, sm_count: Optional[int] = None) -> int:
+    """Particles in one full wave of the production integrator grid (128 particles per CTA x CTAs per SM x SMs):
+    the tcgen05 GMM kernels run 8 (d = 8) / 3 (d = 16, 32) CTAs per SM, the fp32 kernel 4 (2 at d = 32)
+    (csrc/integrator_tc.cu, csrc/integrator.cu launch bounds)."""
+    sms = sm_count if sm_count is not None else L.load().pdeip_sm_count()
+    tensor = path == L.PATH_TENSOR and drift_kind == L.DRIFT_GMM and d in (8, 16, 32) and 1 <= n_gaussian <= 64
+    per_sm = (8 if d == 8 else 3) if tensor else (2 if d >= 32 else 4)
+    return 128 * per_sm * sms
+
+
+def auto_chunk(d: int, n_steps: int, drift_kind: int, n_gaussian: int, path: int, emit_every: int = 1,
+               budget_bytes: float = 6.0e9, sm_count: Optional[int] = None) -> int:
+    """Largest whole number of integrator waves whose [x, v, grad U] trajectory fits `budget_bytes` (at least one wave):
+    no partially filled last wave, and a trajectory buffer far above the 126 MB L2."""
+    wave = integrator_wave(d, drift_kind, n_gaussian, path, sm_count)
+    s_emit = (n_steps + emit_every - 1) // emit_every
+    per_particle = 3 * d * s_emit * 4
+    return wave * max(1, int(budget_bytes // (per_particle * wave)))
+
+
 @dataclass
 class HotPathConfig:
     d: int
@@ -29,7 +49,7 @@ class HotPathConfig:
     drift_kind: int
     n_gaussian: int = 0
     sigma: float = 1.0
-    chunk: int = 1 << 18
+    chunk: int = 0  # particles per integrate -> residual round trip; 0 = auto_chunk(...)
     emit_every: int = 1
     path: int = L.PATH_FP32
 
@@ -37,6 +57,8 @@ class HotPathConfig:
 class HotPath:
     def __init__(self, cfg: HotPathConfig, model, params: Dict, drift_params: Optional[torch.Tensor],
                  true_grad: ops.TrueGrad, optimizer: Optional[AdamL2] = None, device="cuda"):
+        if cfg.chunk <= 0:
+            cfg.chunk = auto_chunk(cfg.d, cfg.n_steps, cfg.drift_kind, cfg.n_gaussian, cfg.path, cfg.emit_every)
         self.cfg, self.model, self.params = cfg, model, params
         self.drift_params, self.true_grad, self.optimizer = drift_params, true_grad, optimizer
         self.device = torch.device(device)

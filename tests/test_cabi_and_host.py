@@ -154,3 +154,23 @@ def test_lyapunov_product_code_matches_oracle_van_loan():
         m1, P1 = o_mom.lyapunov_mean_cov(t, cfg)
         m2, P2 = lyapunov.kinetic_ou_mean_cov(t, cfg)
         assert np.abs(P1 - P2).max() < 1e-9 and np.abs(m1 - m2).max() < 1e-12
+
+
+def test_pipeline_auto_chunk_is_whole_waves():
+    """Host logic of pipeline.auto_chunk: chunks are whole waves of the integrator grid (no GPU needed:
+    pdeip_sm_count() reports 148 without a device) and respect the trajectory-buffer budget."""
+    from pde_inverse_problem_b200 import _lib as L
+    from pde_inverse_problem_b200.pipeline import auto_chunk, integrator_wave
+    assert integrator_wave(8, L.DRIFT_GMM, 16, L.PATH_TENSOR, sm_count=148) == 148 * 8 * 128
+    assert integrator_wave(32, L.DRIFT_GMM, 64, L.PATH_TENSOR, sm_count=148) == 148 * 3 * 128
+    assert integrator_wave(32, L.DRIFT_GMM, 100, L.PATH_TENSOR, sm_count=148) == 148 * 2 * 128  # K > 64: fp32 kernel
+    assert integrator_wave(16, L.DRIFT_LINEAR, 0, L.PATH_TENSOR, sm_count=148) == 148 * 4 * 128
+    c3 = auto_chunk(8, 200, L.DRIFT_GMM, 16, L.PATH_TENSOR, sm_count=148)
+    assert c3 == 2 * 148 * 8 * 128  # 303 104 particles, 5.8 GB: what bench.py uses for C3
+    c5 = auto_chunk(32, 200, L.DRIFT_GMM, 64, L.PATH_TENSOR, sm_count=148)
+    assert c5 == 148 * 3 * 128      # 56 832 particles, 4.4 GB: C5
+    for d, S, kind, K in [(4, 100, L.DRIFT_LINEAR, 0), (16, 100, L.DRIFT_LINEAR, 0), (8, 2000, L.DRIFT_GMM, 16)]:
+        c = auto_chunk(d, S, kind, K, L.PATH_TENSOR, sm_count=148)
+        w = integrator_wave(d, kind, K, L.PATH_TENSOR, sm_count=148)
+        assert c % w == 0 and c >= w and (c == w or 3 * d * S * 4 * c <= 6.0e9)
+    assert auto_chunk(8, 200, L.DRIFT_GMM, 16, L.PATH_TENSOR, sm_count=L.load().pdeip_sm_count()) % 128 == 0
