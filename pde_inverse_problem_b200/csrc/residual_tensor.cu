@@ -84,6 +84,15 @@ struct Cfg {
   static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
 };
 
+#ifndef PDEIP_TC_NLO_FWD
+// Measured (tools/nlo_study.sh, tools/tensor_errors.py): the lo halves matter for the primal stream (it feeds tanh) and
+// for the input-gradient chain (|g|^2 enters the loss); on the tangent streams and the order-1 adjoint they change
+// neither the loss nor the gradient error (1.4e-3 at d = 8 either way) and cost 3 % (8 of the 24 MMAs of P1 + P2).
+#define PDEIP_TC_NLO_FWD 1  // streams of P1 / P2 (primal, order 1, order 2) that get the lo halves of W1 / W2
+#endif
+#ifndef PDEIP_TC_NLO_BWD
+#define PDEIP_TC_NLO_BWD 1  // streams of P3 / P4 (input-gradient chain, order-1 adjoint) that get the lo halves
+#endif
 #ifndef PDEIP_TC_LO_FWD
 #define PDEIP_TC_LO_FWD true  // lo halves of W1, W2 in the forward layer GEMMs P1, P2
 #endif
@@ -181,7 +190,8 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, Desc a, uint32_t a_adv, Des
 
 // NG independent forward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W^T(K-major tile [N][K]), hi + lo halves of
 // the weights, issued round-robin over g.  a_off[g] / d[g]: byte offset of the A band / TMEM column of GEMM g.
-template <int K, int N, int NG, bool LO = true>
+// NLO: the lo weight halves are applied to the first NLO of the NG streams only
+template <int K, int N, int NG, bool LO = true, int NLO = NG>
 __device__ __forceinline__ void mm_fwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi, Desc w_lo) {
   constexpr uint32_t idesc = make_idesc(N, 0, 0);
 #pragma unroll
@@ -192,11 +202,11 @@ __device__ __forceinline__ void mm_fwd(const uint32_t (&d)[NG], Desc a, const ui
 #pragma unroll
     for (int k = 0; k < K; k += 16)
 #pragma unroll
-      for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
+      for (int g = 0; g < NLO; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo, k * 16, idesc, 1u);
   }
 }
 // NG backward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W (transposed view of the weight tile, rows = K)
-template <int K, int N, int NG, bool LO = true>
+template <int K, int N, int NG, bool LO = true, int NLO = NG>
 __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const uint32_t (&a_off)[NG], Desc w_hi_m,
                                        Desc w_lo_m, uint32_t w_rg) {
   constexpr uint32_t idesc = make_idesc(N, 0, 1);
@@ -208,7 +218,7 @@ __device__ __forceinline__ void mm_bwd(const uint32_t (&d)[NG], Desc a, const ui
 #pragma unroll
     for (int k = 0; k < K; k += 16)
 #pragma unroll
-      for (int g = 0; g < NG; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo_m, (k >> 3) * w_rg, idesc, 1u);
+      for (int g = 0; g < NLO; ++g) mma(d[g], a, a_off[g] + k * 16, w_lo_m, (k >> 3) * w_rg, idesc, 1u);
   }
 }
 // band-shifted batch-reduced outer product: D[m][n] += sum_points A[p][a_col0 + m] * B[p][b_col0 + n]
@@ -501,23 +511,23 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
             switch (ph) {
               case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
                 mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
-                mm_fwd<S::KV, 32, 1>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);
+                mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
                 commit(mb);
               } break;
               case 1: {  // z1, z1_1, z2^_1
-                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
+                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD, PDEIP_TC_NLO_FWD>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
               case 2: {  // u, u1, u2^
-                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
+                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD, PDEIP_TC_NLO_FWD>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
               case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
-                mm_bwd<OP, 32, 2>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
+                mm_bwd<OP, 32, 2, true, PDEIP_TC_NLO_BWD>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
               } break;
               case 4: {  // aa1 = za1 W1^T, ab1_1 = zbar1' W1^T;  dW1 += a1_1^T zbar1'
-                mm_bwd<32, 32, 2>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
+                mm_bwd<32, 32, 2, true, PDEIP_TC_NLO_BWD>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
               } break;
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
