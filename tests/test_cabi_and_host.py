@@ -174,3 +174,29 @@ def test_pipeline_auto_chunk_is_whole_waves():
         w = integrator_wave(d, kind, K, L.PATH_TENSOR, sm_count=148)
         assert c % w == 0 and c >= w and (c == w or 3 * d * S * 4 * c <= 6.0e9)
     assert auto_chunk(8, 200, L.DRIFT_GMM, 16, L.PATH_TENSOR, sm_count=L.load().pdeip_sm_count()) % 128 == 0
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver contract of bench.py (CPU arm, runnable without a GPU): stdout carries exactly one JSON line with the
+    reference-arm keys, whatever libraries print (file descriptor 1 is pointed at stderr for the run)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "particle-steps/s" and j["unit"] == "particle-steps/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["n_gpus"] == 1 and j["steps"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"]
+    # ranks other than 0 of a torchrun launch exit 0 without work and without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
+                        capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
