@@ -261,7 +261,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": n * 2 * d * 4, "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / e2e_steps * 1e3},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "mlp_residual_kernel (KFP 0T)", "bound": "tensor", "achieved": res_tflops,
+            "roofline": {"kernel": ("tc::mlp_residual_tc_kernel<%d,%d> (KFP 0T set, tcgen05)" % (8 if d <= 8 else (16 if d <= 16 else 32), 2 if d <= 8 else 1)
+                                    if path == L.PATH_TENSOR else "mlp_residual_kernel<32,2,KFP_0T,8> (fp32)"), "bound": "tensor", "achieved": res_tflops,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
                          "traffic": res_traffic, "traffic_source": res_traffic_src,
                          "peak_source": pk["src"] + " bf16 sustained",
