@@ -84,6 +84,9 @@ struct Cfg {
   static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
 };
 
+#ifndef PDEIP_TC_G_CHAIN_EARLY
+#define PDEIP_TC_G_CHAIN_EARLY 1
+#endif
 #ifndef PDEIP_TC_NLO_FWD
 // Measured (tools/nlo_study.sh, tools/tensor_errors.py): the lo halves matter for the primal stream (it feeds tanh) and
 // for the input-gradient chain (|g|^2 enters the loss); on the tangent streams and the order-1 adjoint they change
@@ -488,6 +491,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     const Desc T2HM = mk_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128), T2LM = mk_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
     constexpr uint32_t CH = 128;  // bytes per chunk (8 operand columns)
     uint32_t dw_started = 0;      // becomes 1 after the first tile's P3..P5 background GEMMs
+    // dW chains whose operands are final before the tail are issued where the tensor pipe idles (P6..P8: 1-2 MMAs per
+    // phase) instead of in the tail P9..P11, which is bound by it: g^^T za0 behind P6's commit, and — two-slot kernel
+    // only: with one slot a chain in front of the next layer GEMM is fully exposed (d = 32: -2.5 %) — c_1^T za1 behind
+    // P7's and c_2^T za2 behind P8's.  d = 8: 2.98e9 -> 3.01e9 evals/s.
+    constexpr bool kCChainsEarly = PDEIP_TC_G_CHAIN_EARLY && NS == 2;
     // NOTE: a compact switch over the phase (about 13 KB of code) measured FASTER than the fully written-out sequence
     // (26 KB): the epilogue warps are instruction-fetch sensitive and the larger MMA stream evicts their code.
     // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
@@ -537,14 +545,27 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
               case 6: {  // zg^_0 = g^ W0
                 mm_fwd<S::KV, 32, 1, false>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
                 commit(mb);
+#if PDEIP_TC_G_CHAIN_EARLY
+                // dW0 += g^^T za0: both operands are final since E6 / E5, and the tensor pipe idles through P6..P8 (1-2
+                // MMAs per phase) while the tail P9..P11 is bound by it: issued here, behind this slot's commit
+                mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+#endif
               } break;
               case 7: {  // zg^_1 = ag^_1 W1  (operand in the a1 band)
                 mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
+                if constexpr (kCChainsEarly) {  // dW1 += c_1^T za1: c_1 is final since E7 (just arrived), za1 since E4
+                  const Desc A1M = mk_desc(sb + S::O_A1, S::RG_A, 128);
+                  mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+                }
               } break;
               case 8: {  // ug^ = ag^_2 W2
                 mm_fwd<32, OP, 1, false>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
                 commit(mb);
+                if constexpr (kCChainsEarly) {  // dW2 += c_2^T za2: c_2 is final since E8 (just arrived), za2 since E3
+                  const Desc A2M = mk_desc(sb + S::O_A2, S::RG_A, 128);
+                  mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+                }
               } break;
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
                 mm_bwd<OP, 32, 2, false>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
@@ -559,7 +580,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #ifdef PDEIP_TC_XLO_DW  // measured: +2 % time, no visible effect on the gradient error (x_lo = x - bf16(x) averages out)
                 mm_outer<32>(TB + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #endif
+#if !PDEIP_TC_G_CHAIN_EARLY
                 mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+#endif
                 commit(mb);  // the next tile's E0 overwrites the x | v bands
               } break;
             }
@@ -589,11 +612,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                   break;
                 case 9:  // dW2 += t2^T s0 + c_2^T za2
                   mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
-                  mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+                  if constexpr (!kCChainsEarly)
+                    mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
                   break;
                 default:  // dW1 += t1^T zbar0' + c_1^T za1
                   mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
-                  mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+                  if constexpr (!kCChainsEarly)
+                    mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
                   break;
               }
             }
