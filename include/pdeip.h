@@ -56,6 +56,10 @@ extern "C" {
 #define PDEIP_DRIFT_GMM       2 /* core/potential.py:32-61, params = mus [K][d] */
 #define PDEIP_DRIFT_MEANFIELD 3 /* grad U = A (x - xbar), params = [A (d*d), xbar (d)] */
 #define PDEIP_DRIFT_IN_POINTS 4 /* residual kernels only: grad V_true is stored after each point's own components */
+#define PDEIP_DRIFT_MEANFIELD_TABLE 5 /* grad U = A (x - xbar_s) at step s (README.md:54-62 with Phi = x'Ax/2 and the EMPIRICAL
+                                         mean of all particles): params = [A (d*d), A xbar_s for s = 0..n_steps ((n_steps+1)*d)]
+                                         from pdeip_meanfield_xbar_table; REFERENCE schedule on the common time grid
+                                         (tau0 == 0 unless injected: step 0 has h = 0, sample s is the state at time s dt) */
 
 /* step schedules */
 #define PDEIP_SCHEDULE_REFERENCE 0 /* step(tau0), (S-1) x step(dt), step(dt - tau0): sampling_utils.py:32-46 */
@@ -127,6 +131,18 @@ int pdeip_kl_integrate_path(const float* z0, float* z_last, float* traj, float* 
                             int schedule, int state_layout, int traj_layout,
                             int emit_every, int emit_offset, int emit_drift, int path, void* stream);
 
+/* Mean-field drift (interacting system, README.md:54-62): the ensemble mean on the common time grid obeys
+ *   pbar' = (1 - gamma dt) pbar + sqrt(2 dt) xibar_s,  qbar' = qbar + dt pbar'   (the interaction cancels in the mean),
+ * xibar_s = mean over ALL particles of the step-s Philox normals.  noise_sums accumulates (atomically, caller zeroes)
+ * sums [(n_steps+1)*d + 2d] doubles over this rank's particles: [s][i] = sum xi_{s,i}, then sum q0 (d), sum p0 (d);
+ * after ONE all-reduce(sum) over ranks, xbar_table turns them into xbar [n_steps+1][d] (nullable; mean position before
+ * step s) and drift_table [n_steps+1][d] = A xbar_s, the tail of the PDEIP_DRIFT_MEANFIELD_TABLE parameter block.
+ * No per-step exchange of sum x is needed: S exchanges collapse into that one all-reduce. */
+int pdeip_meanfield_noise_sums(const float* z0, int64_t n_particles, int d, int n_steps, uint64_t seed,
+                               uint64_t particle_offset, uint32_t step_offset, double* sums, void* stream);
+int pdeip_meanfield_xbar_table(const double* sums, int64_t n_global, int d, int n_steps, float dt, float gamma,
+                               const float* A, float* xbar, float* drift_table, void* stream);
+
 /* the normals / uniforms pdeip_kl_integrate draws in Philox mode (for parity tests):
  * normals [N][n_draws][d] for steps step_offset..step_offset+n_draws-1; uniforms [N] (tau0/dt). */
 int pdeip_philox_normals(float* out, int64_t n_particles, int n_draws, int d, uint64_t seed,
@@ -192,7 +208,8 @@ int pdeip_residual_begin(void* workspace, size_t workspace_bytes, int model_kind
  * true_kind/true_params/true_n_gaussian/true_sigma: drift spec (PDEIP_DRIFT_LINEAR / _GMM / _NONE) of
  *   grad V_true, used by the *_0T kinds for sum|gV_true|^2 and "loss ground truth"; PDEIP_DRIFT_IN_POINTS: the points
  *   carry d extra components holding grad V_true (rows of dim + d floats / dim + d planes).
- * path: PDEIP_PATH_FP32 or PDEIP_PATH_TENSOR (MLP model, KFP kinds only). */
+ * path: PDEIP_PATH_FP32 or PDEIP_PATH_TENSOR (MLP model 32 x 2; KFP_0T and FP_0T run on tcgen05 — FP_0T as d + 1
+ *   direction rows (x, e_i | 0) per point stacked along the GEMM M dimension —, the boundary kinds stay fp32). */
 int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes, int set_kind, int model_kind,
                               const float* params, int d, int hidden, int layers, int n_gaussian,
                               const float* points, int64_t n_points, int layout, float weight, float coef,
@@ -211,6 +228,32 @@ int pdeip_kmv_mean_grad(int model_kind, const float* params, int d, int hidden, 
 int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_bytes, int model_kind, const float* params,
                                   int d, int hidden, int layers, const float* xv, int64_t n, int nt,
                                   const float* G, const float* G_true, const float* c, float weight, void* stream);
+
+/* Reference set != batch: Delta = x[j,t] - ref[i,t], ref [m][nt][2d] (x part used), weight =
+ * 1/(m*n*nt); ref == NULL -> the batch itself (m = n, the reference's choice, kinetic_mckean_vlasov.py:20-23).
+ * A sub-sampled reference set is ref = xv, m < n (the first m trajectories). */
+size_t pdeip_kmv_workspace_bytes_ref(int64_t n, int nt, int d, int64_t m);
+int pdeip_kmv_mean_grad_ref(int model_kind, const float* params, int d, int hidden, int layers,
+                            const float* xv, int64_t n, int nt, const float* ref, int64_t m, float* out_G,
+                            float* out_Gtrue, const float* true_A, void* workspace, size_t workspace_bytes, void* stream);
+int pdeip_residual_accumulate_kmv_ref(void* workspace, size_t workspace_bytes, int model_kind, const float* params,
+                                      int d, int hidden, int layers, const float* xv, int64_t n, int nt,
+                                      const float* ref, int64_t m, const float* G, const float* G_true, const float* c,
+                                      float weight, void* stream);
+/* Moment closure for PDEIP_MODEL_QUADRATIC (Phi = D'W D + b.D): the pair set against the full reference set equals the
+ * pair set against its MEAN (ref = rbar [1][nt][2d], m = 1, weight 1/(n*nt)) plus
+ *   loss += sum_jt 2 c_jt weight tr(W C_t),  dW += sum_jt 2 c_jt weight C_t,   C_t = cov of the reference x at t
+ * (cov [nt][d][d], 1/m normalisation).  O(n) instead of O(n m) at any ensemble size. */
+int pdeip_kmv_closure_correction(void* workspace, size_t workspace_bytes, const float* params, int d, int64_t n, int nt,
+                                 const float* c, const float* cov, float weight, void* stream);
+/* d_s log rho, d_ss log rho of the Gaussian x-marginal and c = d_ss + d_s^2 + gamma d_s on the device
+ * (example_problems/kinetic_mckean_vlasov_example_quadratic.py:51-69,120-177).  coef [nt][3d + 2 + 2d^2] =
+ * [mean1 | a1 | a2 | k1 | k2 | M1 | M2] per time stamp (host float64, once per time stamp):
+ *   d_s = -a1.diff + k1 - diff'M1 diff/2,  d_ss = -a2.diff + k2 - diff'M2 diff/2,  diff = mean1 - x.
+ * xv [n][nt][2d]; outputs (each nullable) are [nt][n] row-major, which the reference reshapes to [n][nt]
+ * (kinetic_mckean_vlasov.py:57-72). */
+int pdeip_kmv_density_terms(const float* xv, int64_t n, int nt, int d, const float* coef, float gamma,
+                            float* out_c, float* out_ps, float* out_ps2, void* stream);
 
 /* loss assembly: loss = G2 - 2 D2 + 2 gamma_or_1 * D1 + GTRUE2 + BOUNDARY  (coefficients already folded in
  * by accumulate, see csrc/residual_common.cuh); sums/grad are device buffers. */
@@ -249,8 +292,11 @@ int pdeip_gather_0T(const float* dataset, int64_t n_traj, int n_time, int dim, c
  * mode 0: D = A B^T (K-major A [128][K], B [N][K]); 1: D = A B (B [K][N], transposed view); 2: D = A^T B
  * (A [K][128], B [K][N], both transposed views); 3: TMEM st/ld round trip.  status (device int) != 0 on timeout.
  * ------------------------------------------------------------------------------------------- */
-/* 0 = every tcgen05 phase of the PDEIP_PATH_TENSOR launches so far completed; 1 = a bounded mbarrier wait timed
- * out (results invalid).  Synchronises the stream. */
+/* Status of the PDEIP_PATH_TENSOR launches since the last query / pdeip_residual_begin: 0 = every tcgen05 phase
+ * completed; bit 0 = a bounded mbarrier wait of the residual kernel timed out, bit 1 = of the integrator (results
+ * invalid).  Read-and-clear; synchronises the stream.  The product path does not need to poll it:
+ * pdeip_residual_begin clears both words and pdeip_residual_finalize writes NaN into sums and grad when either is
+ * set, so the caller's NaN check on the loss (core/trainer.py:112) fires. */
 int pdeip_tensor_path_status(void* stream, int* out_status);
 int pdeip_debug_umma(int mode, const float* A, const float* B, float* D, int K, int N, int* status, void* stream);
 

@@ -25,7 +25,7 @@ class PdeipError(RuntimeError):
 OK = 0
 LAYOUT_AOS, LAYOUT_SOA, LAYOUT_BLOCK128 = 0, 2, 3
 TRAJ_PARTICLE_MAJOR, TRAJ_TIME_MAJOR, TRAJ_TIME_SOA, TRAJ_BLOCK128 = 0, 1, 2, 3
-DRIFT_NONE, DRIFT_LINEAR, DRIFT_GMM, DRIFT_MEANFIELD, DRIFT_IN_POINTS = 0, 1, 2, 3, 4
+DRIFT_NONE, DRIFT_LINEAR, DRIFT_GMM, DRIFT_MEANFIELD, DRIFT_IN_POINTS, DRIFT_MEANFIELD_TABLE = 0, 1, 2, 3, 4, 5
 SCHEDULE_REFERENCE, SCHEDULE_UNIFORM = 0, 1
 MODEL_MLP, MODEL_GMM, MODEL_QUADRATIC = 0, 1, 2
 SET_KFP_0T, SET_KFP_BOUNDARY, SET_FP_0T, SET_FP_BOUNDARY, SET_KMV_PAIRS = 0, 1, 2, 3, 4
@@ -74,6 +74,13 @@ SIGNATURES: Dict[str, tuple] = {
     "pdeip_tensor_path_status": (_i, [_p, _p]),
     "pdeip_debug_umma": (_i, [_i, _p, _p, _p, _i, _i, _p, _p]),
     "pdeip_gather_0T": (_i, [_p, _l, _i, _i, _p, _l, _i, _i, _i, _p, _p]),
+    "pdeip_meanfield_noise_sums": (_i, [_p, _l, _i, _i, _u64, _u64, _u32, _p, _p]),
+    "pdeip_meanfield_xbar_table": (_i, [_p, _l, _i, _i, _f, _f, _p, _p, _p, _p]),
+    "pdeip_kmv_workspace_bytes_ref": (_sz, [_l, _i, _i, _l]),
+    "pdeip_kmv_mean_grad_ref": (_i, [_i, _p, _i, _i, _i, _p, _l, _i, _p, _l, _p, _p, _p, _p, _sz, _p]),
+    "pdeip_residual_accumulate_kmv_ref": (_i, [_p, _sz, _i, _p, _i, _i, _i, _p, _l, _i, _p, _l, _p, _p, _p, _f, _p]),
+    "pdeip_kmv_closure_correction": (_i, [_p, _sz, _p, _i, _l, _i, _p, _p, _f, _p]),
+    "pdeip_kmv_density_terms": (_i, [_p, _l, _i, _i, _p, _f, _p, _p, _p, _p]),
 }
 
 _lib = None

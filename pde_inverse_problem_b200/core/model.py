@@ -69,43 +69,82 @@ class _Model:
         return ops.model_eval(self.spec, self.flat(params), x, want=("grad",))["grad"]
 
 
+KERNEL_HIDDEN = 32  # width the CUDA MLP kernels are built for
+MAX_LAYERS = 8      # deepest stack the fp32 kernels are instantiated for (tensor path: layers == 2)
+
+
 class V_hypothesis(_Model):
-    """core/model.py:32-62: Dense d -> [hidden]*layers -> 40, tanh, V = sum(out^2)."""
+    """core/model.py:32-62: Dense d -> [hidden]*layers -> 40, tanh, V = sum(out^2).
+
+    Supported envelope: one common hidden width <= 32, 1 <= layers <= 8, dim <= 32 (the reference default
+    configurations/neural_network/MLP.yaml is hidden_dim = 20, layers = 8; every script uses 32 x 2).  Narrower
+    widths run on the 32-wide kernels through zero padding: the flat buffer the kernels see is the padded network
+    (kernels [in_pad, out_pad], biases [out_pad]) and the parameter-tree leaves are the reference-shaped sub-views
+    of it.  The padding is exactly invariant: a padded unit has z = 0, a = tanh 0 = 0 and outgoing weights 0, so
+    every gradient entry of the padding is 0 and L2-in-Adam leaves it at 0 (u = 0 / (sqrt 0 + eps))."""
 
     def __init__(self, output_dim: int, hidden_dims, dim: int):
         self.output_dim = output_dim
         self.hidden_dims = list(hidden_dims)
         hs = set(self.hidden_dims)
         if len(hs) != 1:
-            raise NotImplementedError("all hidden layers must share one width")
+            raise NotImplementedError(
+                f"all hidden layers must share one width (got {self.hidden_dims}); supported: one width <= "
+                f"{KERNEL_HIDDEN}, 1 <= layers <= {MAX_LAYERS}")
         self.hidden = self.hidden_dims[0]
         self.layers = len(self.hidden_dims)
         self.dim = dim
-        if self.hidden != 32:
+        if not 1 <= self.hidden <= KERNEL_HIDDEN or not 1 <= self.layers <= MAX_LAYERS:
             raise NotImplementedError(
-                f"the CUDA MLP kernels are built for hidden_dim == 32 (every reference script uses 32); got {self.hidden}")
-        self.spec = ops.ModelSpec(L.MODEL_MLP, dim, self.hidden, self.layers)
+                f"the CUDA MLP kernels support hidden_dim <= {KERNEL_HIDDEN} (zero-padded to {KERNEL_HIDDEN}) and "
+                f"1 <= layers <= {MAX_LAYERS}; got hidden_dim = {self.hidden}, layers = {self.layers}. "
+                f"Set neural_network.hidden_dim / neural_network.layers inside that envelope.")
+        self.spec = ops.ModelSpec(L.MODEL_MLP, dim, KERNEL_HIDDEN, self.layers)
+
+    def _dims(self, hidden):
+        return [self.dim] + [hidden] * self.layers + [OUT_DIM]
 
     def layout(self):
-        dims = [self.dim] + self.hidden_dims + [OUT_DIM]
+        """(name, leaf, shape) of the flat buffer the kernels read (padded widths)."""
+        dims = self._dims(KERNEL_HIDDEN)
         out = []
         for i in range(len(dims) - 1):
             out.append((f"layers_{i}", "kernel", (dims[i], dims[i + 1])))
             out.append((f"layers_{i}", "bias", (dims[i + 1],)))
         return out
 
+    def tree(self, flat: torch.Tensor) -> Dict:
+        t = _tree_from_flat(flat, self.layout())
+        if self.hidden != KERNEL_HIDDEN:  # reference-shaped sub-views of the padded leaves
+            dims = self._dims(self.hidden)
+            for i in range(len(dims) - 1):
+                leaf = t["params"][f"layers_{i}"]
+                leaf["kernel"] = leaf["kernel"][: dims[i], : dims[i + 1]]
+                leaf["bias"] = leaf["bias"][: dims[i + 1]]
+        return t
+
+    def flat(self, params: Dict) -> torch.Tensor:
+        flat = params.get("_flat") if isinstance(params, dict) else None
+        if flat is not None or self.hidden == KERNEL_HIDDEN:
+            return flat_of(params, self.layout())
+        # a foreign reference-shaped tree: scatter it into a zeroed padded buffer
+        dev = params["params"]["layers_0"]["kernel"].device
+        out = self.tree(torch.zeros(self.spec.num_params, device=dev, dtype=torch.float32))
+        for name, leaf in params["params"].items():
+            out["params"][name]["kernel"].copy_(leaf["kernel"])
+            out["params"][name]["bias"].copy_(leaf["bias"])
+        return out["_flat"]
+
     def init(self, rng, x: torch.Tensor) -> Dict:
         """net.init(PRNGKey(11), x): kaiming-normal kernels (std = sqrt(2/fan_in)), zero biases
         (core/model.py:42).  One-off host-side initialisation with torch's generator."""
         g = torch.Generator().manual_seed(int(rng) & 0x7FFFFFFFFFFFFFFF)
-        parts = []
-        for name, leaf, shape in self.layout():
-            if leaf == "kernel":
-                parts.append((torch.randn(shape, generator=g, dtype=torch.float64) * math.sqrt(2.0 / shape[0])).reshape(-1))
-            else:
-                parts.append(torch.zeros(shape, dtype=torch.float64).reshape(-1))
-        flat = torch.cat(parts).float().to(x.device).contiguous()
-        return self.tree(flat)
+        dims = self._dims(self.hidden)
+        tree = self.tree(torch.zeros(self.spec.num_params, device=x.device, dtype=torch.float32))
+        for i in range(len(dims) - 1):
+            w = torch.randn((dims[i], dims[i + 1]), generator=g, dtype=torch.float64) * math.sqrt(2.0 / dims[i])
+            tree["params"][f"layers_{i}"]["kernel"].copy_(w.float())
+        return tree
 
 
 class V_parametric_GMM(_Model):

@@ -40,10 +40,18 @@ int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& 
 int param_eval(int model_kind, const float* params, int d, int n_gaussian, const float* x, const float* v,
                float* out_value, float* out_grad, float* out_vHv, float* out_lap, int64_t n, cudaStream_t st);
 int kmv_mean_grad(int model_kind, const float* params, int d, int hidden, int layers, const float* xv, int64_t n,
-                  int nt, float* out_G, float* out_Gtrue, const float* true_A, void* workspace,
-                  size_t workspace_bytes, cudaStream_t st);
-size_t kmv_ws_bytes(int64_t n, int nt, int d);
+                  int nt, const float* ref, int64_t m, float* out_G, float* out_Gtrue, const float* true_A,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t kmv_ws_bytes(int64_t n, int nt, int d, int64_t m);
+int kmv_closure_correction(const float* W, int d, int64_t n, int nt, const float* c, const float* cov, float weight,
+                           float* part, cudaStream_t st);
+int kmv_density_terms(const float* xv, int64_t n, int nt, int d, const float* coef, float gamma, float* out_c,
+                      float* out_ps, float* out_ps2, cudaStream_t st);
 int kmv_g_sums(const float* G, const float* Gtrue, int64_t n_rows, int d, float w, float* part_sums, cudaStream_t st);
+// residual_tensor.cu: per-device status words of the tcgen05 kernels: [0] residual, [1] integrator (0 = every bounded
+// mbarrier wait completed).  begin clears them, finalize turns a non-zero word into NaN sums / gradient, so that a
+// timed-out phase reaches the caller's existing NaN check (core/trainer.py:112) without an extra host sync.
+int* tensor_status_word();
 
 static int64_t num_params(int model_kind, int d, int hidden, int layers, int n_gaussian) {
   switch (model_kind) {
@@ -59,11 +67,13 @@ static int64_t num_params(int model_kind, int d, int hidden, int layers, int n_g
 }
 
 __global__ void finalize_reduce_kernel(const float* __restrict__ ws, int grid_ctas, int64_t pstride, int64_t P,
-                                       float* __restrict__ sums, float* __restrict__ grad) {
+                                       float* __restrict__ sums, float* __restrict__ grad,
+                                       const int* __restrict__ status) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P + PDEIP_NUM_SUMS) return;
   float s = 0.f;
   for (int b = 0; b < grid_ctas; ++b) s += ws[(int64_t)b * pstride + idx];
+  if (status != nullptr && (status[0] | status[1]) != 0) s = __int_as_float(0x7fc00000);  // a tcgen05 phase timed out
   if (idx < P) grad[idx] = s;
   else if (idx - P != PDEIP_SUM_GRADNORM) sums[idx - P] = s;
 }
@@ -107,6 +117,9 @@ extern "C" int pdeip_residual_begin(void* workspace, size_t workspace_bytes, int
   PDEIP_REQUIRE(workspace != nullptr && workspace_bytes >= residual_ws_bytes(P), PDEIP_ERR_WORKSPACE,
                 "workspace too small: need %zu bytes, got %zu", residual_ws_bytes(P), workspace_bytes);
   PDEIP_CUDA_OK(cudaMemsetAsync(workspace, 0, residual_ws_bytes(P), (cudaStream_t)stream));
+  int* status = tensor_status_word();
+  PDEIP_REQUIRE(status != nullptr, PDEIP_ERR_CUDA, "cannot allocate the tensor-path status words");
+  PDEIP_CUDA_OK(cudaMemsetAsync(status, 0, 2 * sizeof(int), (cudaStream_t)stream));
   return PDEIP_OK;
 }
 
@@ -158,7 +171,8 @@ extern "C" int pdeip_residual_finalize(void* workspace, size_t workspace_bytes, 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = P + PDEIP_NUM_SUMS;
   finalize_reduce_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const float*)workspace, residual_grid(),
-                                                                          residual_pstride(P), P, sums, grad);
+                                                                          residual_pstride(P), P, sums, grad,
+                                                                          tensor_status_word());
   PDEIP_LAUNCH_OK();
   grad_norm_kernel<<<1, 512, 0, st>>>(grad, P, sums);
   PDEIP_LAUNCH_OK();
@@ -178,40 +192,76 @@ extern "C" int pdeip_model_eval(int model_kind, const float* params, int d, int 
   return param_eval(model_kind, params, d, n_gaussian, x, v, out_value, out_grad, out_vHv, out_lap, n, st);
 }
 
-extern "C" size_t pdeip_kmv_workspace_bytes(int64_t n, int nt, int d) {
-  if (n < 1 || nt < 1 || d < 1) return 0;
-  return kmv_ws_bytes(n, nt, d);
+extern "C" size_t pdeip_kmv_workspace_bytes_ref(int64_t n, int nt, int d, int64_t m) {
+  if (n < 1 || nt < 1 || d < 1 || m < 1) return 0;
+  return kmv_ws_bytes(n, nt, d, m);
 }
+extern "C" size_t pdeip_kmv_workspace_bytes(int64_t n, int nt, int d) { return pdeip_kmv_workspace_bytes_ref(n, nt, d, n); }
 
+extern "C" int pdeip_kmv_mean_grad_ref(int model_kind, const float* params, int d, int hidden, int layers,
+                                       const float* xv, int64_t n, int nt, const float* ref, int64_t m, float* out_G,
+                                       float* out_Gtrue, const float* true_A, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  PDEIP_REQUIRE(params && xv && out_G, PDEIP_ERR_INVALID_ARG, "NULL argument");
+  PDEIP_REQUIRE(n >= 1 && nt >= 1, PDEIP_ERR_INVALID_ARG, "n / nt must be >= 1");
+  if (ref == nullptr) { ref = xv; m = n; }
+  PDEIP_REQUIRE(m >= 1, PDEIP_ERR_INVALID_ARG, "reference-set size m must be >= 1");
+  return kmv_mean_grad(model_kind, params, d, hidden, layers, xv, n, nt, ref, m, out_G, out_Gtrue, true_A, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
 extern "C" int pdeip_kmv_mean_grad(int model_kind, const float* params, int d, int hidden, int layers,
                                    const float* xv, int64_t n, int nt, float* out_G, float* out_Gtrue,
                                    const float* true_A, void* workspace, size_t workspace_bytes, void* stream) {
-  PDEIP_REQUIRE(params && xv && out_G, PDEIP_ERR_INVALID_ARG, "NULL argument");
-  PDEIP_REQUIRE(n >= 1 && nt >= 1, PDEIP_ERR_INVALID_ARG, "n / nt must be >= 1");
-  return kmv_mean_grad(model_kind, params, d, hidden, layers, xv, n, nt, out_G, out_Gtrue, true_A, workspace,
-                       workspace_bytes, (cudaStream_t)stream);
+  return pdeip_kmv_mean_grad_ref(model_kind, params, d, hidden, layers, xv, n, nt, nullptr, n, out_G, out_Gtrue, true_A,
+                                 workspace, workspace_bytes, stream);
 }
 
-extern "C" int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_bytes, int model_kind,
-                                             const float* params, int d, int hidden, int layers, const float* xv,
-                                             int64_t n, int nt, const float* G, const float* G_true,
-                                             const float* c, float weight, void* stream) {
+extern "C" int pdeip_residual_accumulate_kmv_ref(void* workspace, size_t workspace_bytes, int model_kind,
+                                                 const float* params, int d, int hidden, int layers, const float* xv,
+                                                 int64_t n, int nt, const float* ref, int64_t m, const float* G,
+                                                 const float* G_true, const float* c, float weight, void* stream) {
   const int64_t P = num_params(model_kind, d, hidden, layers, 0);
   PDEIP_REQUIRE(P > 0, PDEIP_ERR_INVALID_ARG, "unknown model kind %d", model_kind);
   PDEIP_REQUIRE(workspace != nullptr && workspace_bytes >= residual_ws_bytes(P), PDEIP_ERR_WORKSPACE,
                 "workspace too small: need %zu bytes, got %zu", residual_ws_bytes(P), workspace_bytes);
   PDEIP_REQUIRE(params && xv && c, PDEIP_ERR_INVALID_ARG, "NULL argument");
   PDEIP_REQUIRE(n >= 1 && nt >= 1, PDEIP_ERR_INVALID_ARG, "n / nt must be >= 1");
+  if (ref == nullptr) { ref = xv; m = n; }
+  PDEIP_REQUIRE(m >= 1, PDEIP_ERR_INVALID_ARG, "reference-set size m must be >= 1");
   ResidualArgs a;
   memset(&a, 0, sizeof(a));
-  a.params = params; a.points = xv; a.n_points = n * n * nt; a.layout = PDEIP_LAYOUT_AOS; a.d = d;
-  a.layers = layers; a.weight = weight; a.G = G; a.c = c; a.kmv_n = n; a.kmv_nt = nt;
+  a.params = params; a.points = xv; a.n_points = m * n * nt; a.layout = PDEIP_LAYOUT_AOS; a.d = d;
+  a.layers = layers; a.weight = weight; a.G = G; a.c = c; a.ref = ref; a.kmv_n = n; a.kmv_nt = nt;
   a.ws = (float*)workspace; a.pstride = residual_pstride(P);
   cudaStream_t st = (cudaStream_t)stream;
-  if (G) {  // |G|^2, |G_true|^2, |G_true - G|^2 with weight 1/(n*nt) = weight * n
-    int rc = kmv_g_sums(G, G_true, n * nt, d, weight * (float)n, a.ws + P, st);
+  if (G) {  // |G|^2, |G_true|^2, |G_true - G|^2 with weight 1/(n*nt) = weight * m
+    int rc = kmv_g_sums(G, G_true, n * nt, d, weight * (float)m, a.ws + P, st);
     if (rc != PDEIP_OK) return rc;
   }
   if (model_kind == PDEIP_MODEL_MLP) return mlp_residual_accumulate_fp32(PDEIP_SET_KMV_PAIRS, a, hidden, st);
   return param_residual_accumulate(PDEIP_SET_KMV_PAIRS, model_kind, a, 0, st);
+}
+extern "C" int pdeip_residual_accumulate_kmv(void* workspace, size_t workspace_bytes, int model_kind,
+                                             const float* params, int d, int hidden, int layers, const float* xv,
+                                             int64_t n, int nt, const float* G, const float* G_true,
+                                             const float* c, float weight, void* stream) {
+  return pdeip_residual_accumulate_kmv_ref(workspace, workspace_bytes, model_kind, params, d, hidden, layers, xv, n, nt,
+                                           nullptr, n, G, G_true, c, weight, stream);
+}
+
+extern "C" int pdeip_kmv_closure_correction(void* workspace, size_t workspace_bytes, const float* params, int d,
+                                            int64_t n, int nt, const float* c, const float* cov, float weight,
+                                            void* stream) {
+  const int64_t P = num_params(PDEIP_MODEL_QUADRATIC, d, 0, 0, 0);
+  PDEIP_REQUIRE(workspace != nullptr && workspace_bytes >= residual_ws_bytes(P), PDEIP_ERR_WORKSPACE,
+                "workspace too small: need %zu bytes, got %zu", residual_ws_bytes(P), workspace_bytes);
+  PDEIP_REQUIRE(params && c && cov && n >= 1, PDEIP_ERR_INVALID_ARG, "NULL argument / n < 1");
+  return kmv_closure_correction(params, d, n, nt, c, cov, weight, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int pdeip_kmv_density_terms(const float* xv, int64_t n, int nt, int d, const float* coef, float gamma,
+                                       float* out_c, float* out_ps, float* out_ps2, void* stream) {
+  PDEIP_REQUIRE(xv && coef && (out_c || out_ps || out_ps2), PDEIP_ERR_INVALID_ARG, "NULL argument");
+  PDEIP_REQUIRE(n >= 1 && nt >= 1, PDEIP_ERR_INVALID_ARG, "n / nt must be >= 1");
+  return kmv_density_terms(xv, n, nt, d, coef, gamma, out_c, out_ps, out_ps2, (cudaStream_t)stream);
 }

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
   // stage the drift parameters (zero-padded to DP) in shared memory
   float* A_s = smem;           // LINEAR / MEANFIELD: [DP][DP] (+ [DP] shift)
   float* shift_s = nullptr;
-  if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+  constexpr bool kTable = DRIFT == PDEIP_DRIFT_MEANFIELD_TABLE;  // grad U = A x - (A xbar_s), row s of the table per step
+  if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD || kTable) {
     load_padded<DP>(A_s, a.drift_params, a.d, a.d, threadIdx.x, blockDim.x);
     // rows >= d must be zero too
     for (int idx = a.d * DP + threadIdx.x; idx < DP * DP; idx += blockDim.x) A_s[idx] = 0.0f;
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
   const bool ref_sched = (a.schedule == PDEIP_SCHEDULE_REFERENCE);
   float t0 = 0.0f;
   if (ref_sched) {
-    t0 = a.tau0 ? a.tau0[n] : philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
+    // mean-field table: a common time grid (tau0 == 0) unless the caller injects tau0
+    t0 = a.tau0 ? a.tau0[n] : (kTable ? 0.0f : philox_uniform01(a.seed, pid, kTagTau0) * a.dt);  // sampling_utils.py:32
   }
   const int total_steps = ref_sched ? a.n_steps + 1 : a.n_steps;
   const int n_draws = total_steps;
@@ -142,8 +144,14 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
     float g[DP];
     if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
       gmm_grad_thread<DP>(q, smem, a.n_gaussian, a.inv_sigma2, g);
-    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD || kTable) {
       linear_grad_thread<DP>(q, A_s, shift_s, g);
+      if constexpr (kTable) {
+        const float* row = a.drift_params + d * d + (int64_t)s * d;
+#pragma unroll
+        for (int i = 0; i < DP; ++i)
+          if (i < d) g[i] -= __ldg(row + i);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < DP; ++i) g[i] = 0.0f;
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(128) kl_integrate_kernel(const IntegrateArgs a
     float g[DP];
     if constexpr (DRIFT == PDEIP_DRIFT_GMM) {
       gmm_grad_thread<DP>(q, smem, a.n_gaussian, a.inv_sigma2, g);
-    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD) {
+    } else if constexpr (DRIFT == PDEIP_DRIFT_LINEAR || DRIFT == PDEIP_DRIFT_MEANFIELD || kTable) {
       linear_grad_thread<DP>(q, A_s, shift_s, g);
     } else {
 #pragma unroll
@@ -332,7 +340,8 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
       p[2 * i4] = make_float2(tp.x, tp.y); p[2 * i4 + 1] = make_float2(tp.z, tp.w);
     }
   }
-  const float t0 = philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
+  constexpr bool kTable = DRIFT == PDEIP_DRIFT_MEANFIELD_TABLE;  // common time grid: tau0 == 0
+  const float t0 = kTable ? 0.f : philox_uniform01(a.seed, pid, kTagTau0) * a.dt;  // sampling_utils.py:32
   const float c2 = -0.5f * a.inv_sigma2 * 1.4426950408889634f;
   const int S = a.n_steps;
   // BLK: element (sample s, block b, component c, lane l) at ((s B + b) 3d + c) 128 + l ; else c S N + s N + n
@@ -345,6 +354,12 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
     float2 g[DP / 2];
     if constexpr (DRIFT == PDEIP_DRIFT_GMM) gmm_grad_fast<DP>(q, smem, k_pad, c2, a.inv_sigma2, g);
     else linear_grad_fast<DP>(q, smem, g);
+    if constexpr (kTable) {  // grad U = A (x - xbar_s): row s of the (A xbar) table (warp-uniform address)
+      const float2* row = reinterpret_cast<const float2*>(a.drift_params + DP * DP + (int64_t)s * DP);
+      const float2 neg1 = make_float2(-1.f, -1.f);
+#pragma unroll
+      for (int i = 0; i < DP / 2; ++i) g[i] = __ffma2_rn(__ldg(row + i), neg1, g[i]);
+    }
     if (s >= 1) {  // grad U at the state emitted as sample s - 1
       float* og = o - sstride + 2 * DP * plane;
 #pragma unroll
@@ -407,7 +422,8 @@ __global__ void __launch_bounds__(128, DP >= 32 ? 2 : PDEIP_FAST_MINB) kl_integr
 
 // true if the call is the production configuration served by kl_integrate_fast_kernel
 static bool fast_path_ok(const IntegrateArgs& a, int drift_kind, int DP) {
-  return a.d == DP && DP % 4 == 0 && (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR) && !a.noise &&
+  return a.d == DP && DP % 4 == 0 &&
+         (drift_kind == PDEIP_DRIFT_GMM || drift_kind == PDEIP_DRIFT_LINEAR || drift_kind == PDEIP_DRIFT_MEANFIELD_TABLE) && !a.noise &&
          !a.tau0 && !a.tau && a.traj && a.z_last && a.emit_drift && a.emit_every == 1 && a.emit_offset == 0 &&
          a.schedule == PDEIP_SCHEDULE_REFERENCE && a.state_layout == PDEIP_LAYOUT_AOS &&
          (a.traj_layout == PDEIP_TRAJ_TIME_SOA || a.traj_layout == PDEIP_TRAJ_BLOCK128) &&
@@ -427,6 +443,11 @@ static int launch_integrate_fast(const IntegrateArgs& a, int drift_kind, cudaStr
         kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM, true><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
       else
         kl_integrate_fast_kernel<DP, PDEIP_DRIFT_GMM, false><<<(unsigned)grid, block, smem, st>>>(a, k_pad);
+    } else if (drift_kind == PDEIP_DRIFT_MEANFIELD_TABLE) {
+      if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_MEANFIELD_TABLE, true><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
+      else
+        kl_integrate_fast_kernel<DP, PDEIP_DRIFT_MEANFIELD_TABLE, false><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
     } else {
       if (a.traj_layout == PDEIP_TRAJ_BLOCK128)
         kl_integrate_fast_kernel<DP, PDEIP_DRIFT_LINEAR, true><<<(unsigned)grid, block, sizeof(float) * DP * DP, st>>>(a, 0);
@@ -461,6 +482,12 @@ static int launch_integrate(const IntegrateArgs& a, int drift_kind, int path, cu
     case PDEIP_DRIFT_MEANFIELD:
       smem = sizeof(float) * (DP * DP + DP);
       kl_integrate_kernel<DP, PDEIP_DRIFT_MEANFIELD><<<(unsigned)grid, block, smem, st>>>(a);
+      break;
+    case PDEIP_DRIFT_MEANFIELD_TABLE:
+      PDEIP_REQUIRE(a.schedule == PDEIP_SCHEDULE_REFERENCE, PDEIP_ERR_UNSUPPORTED,
+                    "PDEIP_DRIFT_MEANFIELD_TABLE needs the REFERENCE schedule (table row = step index)");
+      smem = sizeof(float) * DP * DP;
+      kl_integrate_kernel<DP, PDEIP_DRIFT_MEANFIELD_TABLE><<<(unsigned)grid, block, smem, st>>>(a);
       break;
     case PDEIP_DRIFT_GMM:
       smem = sizeof(float) * (size_t)a.n_gaussian * DP;
@@ -502,6 +529,94 @@ __global__ void philox_raw_kernel(const uint32_t* ctr, const uint32_t* key, uint
   uint32_t c0 = ctr[4 * i], c1 = ctr[4 * i + 1], c2 = ctr[4 * i + 2], c3 = ctr[4 * i + 3];
   philox4x32_10(c0, c1, c2, c3, key[0], key[1]);
   out[4 * i] = c0; out[4 * i + 1] = c1; out[4 * i + 2] = c2; out[4 * i + 3] = c3;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Mean-field drift  grad U = A (x - xbar_t),  xbar_t = empirical mean over ALL particles of all ranks  (README.md:54-62:
+// -grad Phi * rho_t for Phi = x'Ax/2).  On the common time grid (tau0 == 0: step 0 has h = 0, steps 1..S have h = dt) the
+// ensemble mean obeys a closed recursion, because the interaction term A (xbar - xbar) vanishes in the mean:
+//     pbar_{s+1} = (1 - gamma dt) pbar_s + sqrt(2 dt) xibar_s,   qbar_{s+1} = qbar_s + dt pbar_{s+1},
+// xibar_s = mean over particles of the step-s normals.  The noise is counter-based (Philox keyed by the global particle
+// id), so xibar_s for ALL steps comes from one pre-pass over the particles, ONE all-reduce of (S+1) d + 2 d doubles
+// replaces S per-step exchanges of sum x, and the integrator itself runs without any synchronisation.  The table is
+// exactly what per-step recomputation gives in exact arithmetic (rounding differs at 1e-7; tests compare with the
+// oracle's per-step empirical mean).
+// ------------------------------------------------------------------------------------------------------------
+// sums [(n_draws) d + 2 d] doubles, accumulated with atomics (caller zeroes): [s][i] sum xi_{s,i};  tail: sum q0, sum p0
+__global__ void __launch_bounds__(256) meanfield_noise_sums_kernel(const float* __restrict__ z0, int64_t n, int d,
+                                                                   int n_draws, uint64_t seed, uint64_t particle_offset,
+                                                                   uint32_t step_offset, double* __restrict__ sums) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int s = -1; s < n_draws; ++s) {  // s == -1: the initial state sums (2 passes of up to 32 components)
+    for (int half = 0; half < (s < 0 ? 2 : 1); ++half) {
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      for (int64_t p = first; p < n; p += stride) {
+        if (s < 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < d) acc[i] += z0[p * 2 * d + half * d + i];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (4 * j < d) {
+              float r4[4];
+              philox_normal4(seed, particle_offset + (uint64_t)p, step_offset + (uint32_t)s, (uint32_t)j, r4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (4 * j + k < d) acc[4 * j + k] += r4[k];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < d) {
+          const float w = warp_sum(acc[i]);
+          if (lane == 0) red[warp][i] = w;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < d) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)red[w][threadIdx.x];
+        double* dst = s < 0 ? sums + (int64_t)n_draws * d + half * d : sums + (int64_t)s * d;
+        atomicAdd(dst + threadIdx.x, t);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// one block, d <= 32 threads active: xbar [n_draws][d] (mean position BEFORE step s) and shift [n_draws][d] = A xbar_s
+__global__ void meanfield_xbar_table_kernel(const double* __restrict__ sums, double inv_n, int d, int n_draws, double dt,
+                                            double gamma, const float* __restrict__ A, float* __restrict__ xbar,
+                                            float* __restrict__ shift) {
+  __shared__ double qs[32];
+  const int i = threadIdx.x;
+  double q = 0.0, p = 0.0;
+  if (i < d) {
+    q = sums[(int64_t)n_draws * d + i] * inv_n;
+    p = sums[(int64_t)n_draws * d + d + i] * inv_n;
+  }
+  for (int s = 0; s < n_draws; ++s) {
+    if (i < d) qs[i] = q;
+    __syncthreads();
+    if (i < d) {
+      if (xbar) xbar[(int64_t)s * d + i] = (float)q;
+      double a = 0.0;
+      for (int k = 0; k < d; ++k) a += (double)A[i * d + k] * qs[k];
+      shift[(int64_t)s * d + i] = (float)a;
+      const double h = s == 0 ? 0.0 : dt;  // tau0 == 0: the first step of the reference schedule has h = 0
+      p = (1.0 - gamma * h) * p + sqrt(2.0 * h) * (sums[(int64_t)s * d + i] * inv_n);
+      q += h * p;
+    }
+    __syncthreads();
+  }
 }
 
 // z = mu + cov_half xi   (core/distribution.py:64-65); one thread per sample, dim <= 64
@@ -627,6 +742,32 @@ extern "C" int pdeip_gaussian_sample(float* out, int64_t n, int dim, const float
   if (n == 0) return PDEIP_OK;
   gaussian_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       out, n, dim, mu, cov_half, seed, particle_offset, layout);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+extern "C" int pdeip_meanfield_noise_sums(const float* z0, int64_t n_particles, int d, int n_steps, uint64_t seed,
+                                          uint64_t particle_offset, uint32_t step_offset, double* sums, void* stream) {
+  PDEIP_REQUIRE(z0 && sums, PDEIP_ERR_INVALID_ARG, "NULL argument");
+  PDEIP_REQUIRE(n_particles >= 0 && d >= 1 && d <= 32 && n_steps >= 1, PDEIP_ERR_UNSUPPORTED,
+                "meanfield_noise_sums supports 1 <= d <= 32, n_steps >= 1");
+  if (n_particles == 0) return PDEIP_OK;
+  int64_t blocks = (n_particles + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  meanfield_noise_sums_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z0, n_particles, d, n_steps + 1, seed,
+                                                                                 particle_offset, step_offset, sums);
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
+extern "C" int pdeip_meanfield_xbar_table(const double* sums, int64_t n_global, int d, int n_steps, float dt, float gamma,
+                                          const float* A, float* xbar, float* drift_table, void* stream) {
+  PDEIP_REQUIRE(sums && A && drift_table, PDEIP_ERR_INVALID_ARG, "NULL argument");
+  PDEIP_REQUIRE(n_global >= 1 && d >= 1 && d <= 32 && n_steps >= 1, PDEIP_ERR_UNSUPPORTED,
+                "meanfield_xbar_table supports 1 <= d <= 32, n_steps >= 1, n_global >= 1");
+  meanfield_xbar_table_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, 1.0 / (double)n_global, d, n_steps + 1, (double)dt,
+                                                                  (double)gamma, A, xbar, drift_table);
   PDEIP_LAUNCH_OK();
   return PDEIP_OK;
 }

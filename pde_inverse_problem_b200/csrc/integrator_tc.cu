@@ -626,6 +626,7 @@ bool integrate_tensor_ok(const IntegrateArgs& a, int drift_kind) {
 int launch_integrate_tensor(const IntegrateArgs& a, cudaStream_t st) {
   int* status = tensor_status_word();
   PDEIP_REQUIRE(status != nullptr, PDEIP_ERR_CUDA, "cannot allocate the tensor-path status word");
+  status += 1;  // word 1: integrator (word 0: residual kernel)
   const int kp = (a.n_gaussian + 15) / 16 * 16;
   if (a.d == 8) {
     if (kp == 16) return itc::launch8<16>(a, status, st);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kPNW * 32, 1) quad_param_residual_kernel(const
       const int64_t ij = pp / nt;
       const int64_t j = ij % n, i = ij / n;
       const float* rj = a.points + (j * nt + t) * 2 * d;
-      const float* ri = a.points + (i * nt + t) * 2 * d;
+      const float* ri = (a.ref ? a.ref : a.points) + (i * nt + t) * 2 * d;
       for (int c = 0; c < d; ++c) {
         y[c] = valid ? rj[c] - ri[c] : 0.f;
         v[c] = valid ? rj[d + c] : 0.f;

@@ -38,11 +38,14 @@ struct ResidualArgs {
   TrueGrad tg;
   float* ws;       // this launch's workspace
   int64_t pstride;
-  // KMV pairs
+  // KMV pairs: Delta = x[j,t] - ref[i,t], j < kmv_n, i < (n_points / (kmv_n * kmv_nt)); ref == NULL: the batch itself
   const float* G;
   const float* c;
+  const float* ref;
   int64_t kmv_n;
   int kmv_nt;
+  // tensor path, FP 0T set: fp_dirs = d + 1 virtual (x, direction) rows per point (0: kinetic point set)
+  int fp_dirs;
 };
 
 // grad V_true at x (runtime d), parameters in shared memory (unpadded)

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp_residual_kernel(const Residual
       const int64_t ij = pp / nt;
       const int64_t j = ij % n, i = ij / n;
       const float* rj = a.points + (j * nt + t) * 2 * d;
-      const float* ri = a.points + (i * nt + t) * 2 * d;
+      const float* ri = (a.ref ? a.ref : a.points) + (i * nt + t) * 2 * d;
       for (int c = 0; c < d; ++c) {
         st.x[c] = valid ? rj[c] - ri[c] : 0.f;
         v[c] = valid ? rj[d + c] : 0.f;
@@ -235,11 +235,12 @@ static int launch_mlp_residual(int set_kind, const ResidualArgs& a, cudaStream_t
 int mlp_residual_accumulate_fp32(int set_kind, const ResidualArgs& a, int hidden, cudaStream_t st) {
   PDEIP_REQUIRE(hidden == 32, PDEIP_ERR_UNSUPPORTED,
                 "fp32 MLP residual is built for hidden_dim == 32 (pad smaller widths with zeros); got %d", hidden);
-  PDEIP_REQUIRE(a.layers >= 1 && a.layers <= 4, PDEIP_ERR_UNSUPPORTED, "1 <= layers <= 4 supported (got %d)",
+  PDEIP_REQUIRE(a.layers >= 1 && a.layers <= 8, PDEIP_ERR_UNSUPPORTED, "1 <= layers <= 8 supported (got %d)",
                 a.layers);
   PDEIP_REQUIRE(a.d >= 1 && a.d <= kDMax, PDEIP_ERR_UNSUPPORTED, "1 <= d <= %d supported (got %d)", kDMax, a.d);
   if (a.layers <= 2) return launch_mlp_residual<32, 2, 8>(set_kind, a, st);
-  return launch_mlp_residual<32, 4, 4>(set_kind, a, st);
+  if (a.layers <= 4) return launch_mlp_residual<32, 4, 4>(set_kind, a, st);
+  return launch_mlp_residual<32, 8, 4>(set_kind, a, st);  // configurations/neural_network/MLP.yaml: layers = 8
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,15 +293,17 @@ int mlp_eval_fp32(const float* params, int d, int hidden, int layers, const floa
                   float* out_value, float* out_grad, float* out_vHv, float* out_lap, int64_t n,
                   cudaStream_t st) {
   PDEIP_REQUIRE(hidden == 32, PDEIP_ERR_UNSUPPORTED, "model_eval is built for hidden_dim == 32 (got %d)", hidden);
-  PDEIP_REQUIRE(layers >= 1 && layers <= 4, PDEIP_ERR_UNSUPPORTED, "1 <= layers <= 4 supported (got %d)", layers);
+  PDEIP_REQUIRE(layers >= 1 && layers <= 8, PDEIP_ERR_UNSUPPORTED, "1 <= layers <= 8 supported (got %d)", layers);
   PDEIP_REQUIRE(d >= 1 && d <= kDMax, PDEIP_ERR_UNSUPPORTED, "1 <= d <= %d supported (got %d)", kDMax, d);
   const MlpShape<32> sh{d, layers};
   const size_t smem = sizeof(float) * (size_t)sh.num_params();
   const unsigned grid = (unsigned)((n + 127) / 128);
   if (layers <= 2) {
     mlp_eval_kernel<32, 2><<<grid, 128, smem, st>>>(params, d, layers, x, v, out_value, out_grad, out_vHv, out_lap, n);
-  } else {
+  } else if (layers <= 4) {
     mlp_eval_kernel<32, 4><<<grid, 128, smem, st>>>(params, d, layers, x, v, out_value, out_grad, out_vHv, out_lap, n);
+  } else {
+    mlp_eval_kernel<32, 8><<<grid, 128, smem, st>>>(params, d, layers, x, v, out_value, out_grad, out_vHv, out_lap, n);
   }
   PDEIP_LAUNCH_OK();
   return PDEIP_OK;

@@ -26,6 +26,15 @@
 //           P5 g (+dW0: v) | P6 zg^_0 | P7 zg^_1 | P8 ug^ | P9 ab_2, aa2 (+dW2: t, c) | P10 ab_1, aa1 (+dW1: t, c) |
 //           P11 (dW0: x_hi, x_lo, g^).   E_k = epilogue between P_{k-1} and P_k.
 //   parity  rtol 1e-2 (BASELINE.json, bf16 GEMM path); measured against the oracle in tests/test_gpu_tensor.py.
+//
+// FP 0T set (methods/consistency_instances/fokker_planck.py:33-63: |g|^2 - 2 sum_i D_{e_i}^2 V, the d forward-mode
+// tangents of jacfwd(grad V)) on the same kernel: the d tangent streams e_1..e_d of a point are STACKED ALONG M as d
+// rows (x, v = e_i) of the tile, plus one row (x, v = 0) of weight -(d - 1).  With gamma = 0 a row contributes
+// l(x, v) = |g|^2 - 2 D_v^2 V, so  sum_i l(x, e_i) - (d - 1) l(x, 0) = |g|^2 - 2 Laplacian V  and the same combination
+// of the parameter gradients (every per-row quantity is linear in the row weight `mk`).  The |g|^2 parts cancel
+// exactly: rows of the same x run the same instructions on the same operands.  a.fp_dirs = d + 1 virtual rows per
+// point; row p is (point p / (d+1), direction p % (d+1)).  Cost: (d + 1) KFP evaluations per point (the primal and
+// the g-stream are recomputed per direction: 2x the algorithmic FLOPs of a shared-primal kernel).
 #include "mlp_thread.cuh"
 #include "residual_common.cuh"
 #include "umma.cuh"
@@ -411,7 +420,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   // Every CTA owns a CONTIGUOUS range of tiles (a multiple of NS): its input stream walks one region of the point set
   // front to back (one new 2 MB page every ~170 tiles at d = 8 instead of every tile with a grid-strided assignment).
   // n_tiles is the END of this CTA's range.
-  const int64_t n_tiles_all = (a.n_points + 127) / 128;
+  const int fpd = a.fp_dirs;                                                   // 0: kinetic rows (x, v)
+  const int64_t n_rows = fpd ? a.n_points * fpd : a.n_points;                 // (virtual) rows of this point set
+  const int64_t n_tiles_all = (n_rows + 127) / 128;
   const int64_t per_cta = ((n_tiles_all + gridDim.x - 1) / gridDim.x + NS - 1) / NS * NS;
   const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
   if (tile_begin >= n_tiles_all) return;  // nothing to do for this CTA (uniform)
@@ -646,7 +657,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     for (int i = 0; i < 24; ++i) db2[i] = 0.f;
     float sum_g2 = 0.f, sum_gt2 = 0.f, sum_gd2 = 0.f, sum_d1 = 0.f, sum_d2 = 0.f;
     const float gamma = a.coef, gamma4 = 4.f * a.coef;
-    const int dimw = 2 * d + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
+    const int dimw = (fpd ? d : 2 * d) + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
     // byte offsets of this thread's row inside the operand tiles (chunk c adds c * 128)
     const uint32_t offX = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_X;
     const uint32_t offA = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_A;
@@ -659,18 +670,23 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     auto load_into = [&](float (&xin)[NI][8], int64_t t) {
       const int64_t cstride = comp_stride(a.layout, a.n_points);
       const int64_t pp = t * 128 + row;
-      const int64_t pc = (t < n_tiles && pp < a.n_points) ? pp : 0;
+      const int64_t pr = (t < n_tiles && pp < n_rows) ? pp : 0;
+      const int64_t pc = fpd ? pr / fpd : pr;                 // FP: row -> (point, direction)
+      const int dir = fpd ? (int)(pr - pc * fpd) : -1;
       const float* const pbase = a.points + point_base(a.layout, pc, dimw);
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int j = half + 2 * i;
         const int band = (j / S::XC) < 3 ? (j / S::XC) : 0, cg = j % S::XC;
         const int bandc = (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS) ? band : 0;
+        // FP rows hold [x (d), grad V_true (d, IN_POINTS)]: the gt band sits right after x, the v band is e_dir
+        const int bandm = fpd ? (bandc == 2 ? 1 : 0) : bandc;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int u = cg * 8 + e;
           const int uc = u < d ? u : 0;
-          xin[i][e] = __ldg(pbase + (bandc * d + uc) * cstride);
+          const float val = __ldg(pbase + (bandm * d + uc) * cstride);
+          xin[i][e] = (fpd && band == 1) ? (u == dir ? 1.f : 0.f) : val;
         }
       }
     };
@@ -688,7 +704,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // destination register, nothing to wait for; prefetch.global.L2 = CCTL.PF2 measured ~700 cycles per phase) and E0
     // issues the loads itself, before its commit wait: they hit L2 and land behind that wait.
     auto prefetch_inputs = [&](int64_t t) {
-      if (t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // ragged last tile: not worth a special case
+      if (fpd || t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // FP rows / ragged last tile: not worth a special case
       if (a.layout == PDEIP_LAYOUT_SOA) {  // dimw component segments of 512 B
         if ((a.n_points & 3) == 0 && half == 0 && row < dimw)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.points + (int64_t)row * a.n_points + t * 128),
@@ -719,9 +735,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z + offZ;
       const uint32_t LA = LA0 + (uint32_t)s * SLOT_COLS;
       const int64_t tile = base + s;
-      const int64_t p = tile * 128 + row;
-      const bool valid = tile < n_tiles && p < a.n_points;
-      const float mk = valid ? 1.f : 0.f;
+      const int64_t prow = tile * 128 + row;
+      const bool valid = tile < n_tiles && prow < n_rows;
+      const int64_t p = fpd ? prow / fpd : prow;  // point index of this row
+      // row weight: 1, or for the FP direction rows  +1 (v = e_i) / -(d - 1) (v = 0)
+      const float mk = !valid ? 0.f : ((fpd && prow - p * fpd == fpd - 1) ? -(float)(fpd - 2) : 1.f);
 #ifdef PDEIP_TC_PROBE
       const bool probe_on = blockIdx.x == 0 && tile == 0;
 #endif
@@ -939,15 +957,17 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
             float g4[8], gv[8], gt[8];
             tm_ld8(LA + C_G + 8 * cg, reinterpret_cast<uint32_t*>(g4));
             tm_wait_ld();
+            // the chain za^ carries the row weight mk (it seeds the adjoints): g itself is weight-free
+            const float gsc = mk != 0.f ? 0.25f / mk : 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              gv[e] = 0.25f * g4[e];
+              gv[e] = gsc * g4[e];
               gt[e] = 0.f;
             }
             if (band == 0) {
               float gh[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) gh[e] = 0.125f * g4[e];
+              for (int e = 0; e < 8; ++e) gh[e] = 0.5f * gv[e];
               put_chunk(X, (S::XC_G + cg) * 128, gh);
               TC_PROBE(15, cg * 8, gv, 8);
             }
@@ -1003,7 +1023,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
         TC_PROBE(l1 ? 16 : 17, u16, cc, 16);
       } else if constexpr (ph == 9) {
-        // E9: s0 = s0p + 8 ug^;  db2 += s0
+        // E9: s0 = s0p + 8 mk ug^;  db2 += s0
         float ug[24], s0[24];
         uint32_t spp[12];
         tm_ldp<24>(LA + C_S0P + 12 * half, spp);
@@ -1014,14 +1034,14 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #if PDEIP_TC_PACKED
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-          const float2 v = __ffma2_rn(bc2(8.f), pr(ug, i), unp2(spp, i));
+          const float2 v = __ffma2_rn(bc2(8.f * mk), pr(ug, i), unp2(spp, i));  // the g-stream is weight-free: weight its seed
           st2(s0, i, v);
           st2(db2, i, __fadd2_rn(pr(db2, i), v));
         }
 #else
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
-          s0[i] = fmaf(8.f, ug[i], unp(spp, i));
+          s0[i] = fmaf(8.f * mk, ug[i], unp(spp, i));
           db2[i] += s0[i];
         }
 #endif
@@ -1174,7 +1194,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         part[P + PDEIP_SUM_G2] += g2;
         part[P + PDEIP_SUM_GTRUE2] += gt2;
         part[P + PDEIP_SUM_GT] += gd2;
-        part[P + PDEIP_SUM_D1] += D1;
+        if (!fpd) part[P + PDEIP_SUM_D1] += D1;  // FP rows: D_{e_i} V is not a loss term (fokker_planck.py:50-51)
         part[P + PDEIP_SUM_D2] += D2;
         part[P + PDEIP_SUM_LOSS] += g2 + gt2 - 2.f * D2 + 2.f * gamma * D1;
       }
@@ -1216,7 +1236,13 @@ static int launch_tc(const ResidualArgs& a, int* status, cudaStream_t st) {
 
 int mlp_residual_accumulate_tensor(int set_kind, const ResidualArgs& a, int hidden, cudaStream_t st) {
   // boundary sets (two launches over n points vs n*S points of the 0T set) stay on the fp32 kernel
-  if (set_kind != PDEIP_SET_KFP_0T) return mlp_residual_accumulate_fp32(set_kind, a, hidden, st);
+  if (set_kind != PDEIP_SET_KFP_0T && set_kind != PDEIP_SET_FP_0T) return mlp_residual_accumulate_fp32(set_kind, a, hidden, st);
+  if (set_kind == PDEIP_SET_FP_0T) {  // d tangent streams stacked along M: d + 1 rows (x, e_i | 0) per point, gamma = 0
+    ResidualArgs f = a;
+    f.fp_dirs = a.d + 1;
+    f.coef = 0.f;
+    return mlp_residual_accumulate_tensor(PDEIP_SET_KFP_0T, f, hidden, st);
+  }
   PDEIP_REQUIRE(hidden == 32 && a.layers == 2, PDEIP_ERR_UNSUPPORTED,
                 "tensor path is built for hidden_dim == 32, layers == 2 (got %d, %d)", hidden, a.layers);
   PDEIP_REQUIRE(a.d >= 1 && a.d <= 32, PDEIP_ERR_UNSUPPORTED, "tensor path supports 1 <= d <= 32 (got %d)", a.d);
@@ -1228,11 +1254,15 @@ int mlp_residual_accumulate_tensor(int set_kind, const ResidualArgs& a, int hidd
 }
 #endif
 
+// read-and-clear: bit 0 = a residual phase timed out, bit 1 = an integrator phase timed out since the last query / begin
 int tensor_path_status(cudaStream_t st, int* out) {
   int* status = tensor_status_word();
   if (!status) return PDEIP_ERR_CUDA;
-  if (cudaMemcpyAsync(out, status, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return PDEIP_ERR_CUDA;
+  int w[2] = {0, 0};
+  if (cudaMemcpyAsync(w, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return PDEIP_ERR_CUDA;
   if (cudaStreamSynchronize(st) != cudaSuccess) return PDEIP_ERR_CUDA;
+  *out = (w[0] ? 1 : 0) | (w[1] ? 2 : 0);
+  if (*out && cudaMemsetAsync(status, 0, 2 * sizeof(int), st) != cudaSuccess) return PDEIP_ERR_CUDA;
   return PDEIP_OK;
 }
 

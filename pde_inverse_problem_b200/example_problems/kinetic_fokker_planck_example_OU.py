@@ -132,6 +132,7 @@ class KineticFokkerPlanck(ProblemInstance):
             raise NotImplementedError
         rng_time_shift, rng = jrandom.split(rng)
         ts = self._grid_times(rng_time_shift, batch_size[0])
+        self.last_grid_times_host = [float(t) for t in ts]  # the same stamps as Python floats: no device read later
         return torch.as_tensor(ts, dtype=torch.float32, device=self.device)
 
     def create_parametric_model(self):

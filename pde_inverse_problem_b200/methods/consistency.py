@@ -58,6 +58,9 @@ class ConsistencyBased(Method):
                 }
                 if isinstance(bs, tuple):  # the reference calls this for every mode; only grid_time implements it
                     data["tau_0T"] = pde.get_time_sample_ground_truth(rng_0T, bs)
+                    host = getattr(pde, "last_grid_times_host", None)
+                    if host is not None:  # KMV residual: per-time-stamp coefficients are looked up on the host
+                        data["tau_0T_host"] = host
             elif pde.sample_scheme == "SDE":
                 data = {}
                 data["initial"], data["terminal"], data["0T"] = pde.sample_ground_truth(

@@ -23,13 +23,15 @@ def value_and_grad_fn(forward_fn, params, data, rng, pde_instance, path=None):
     xv = data["0T"].reshape(-1, nt, 2 * d).contiguous()
     n = xv.shape[0]
     gamma = float(pde_instance.initial_configuration["gamma_friction"])
-    # time derivatives of log rho at every (sample, time stamp): vmap over (tau, x[:, t]) gives [nt, n]; the
-    # reference then *reshapes* to [n, nt] (:57-72, defect D4 kept: identical for nt == 1)
-    psl = torch.stack([pde_instance.partial_s_log_density_fn(tau[t], xv[:, t, :d]) for t in range(nt)], 0).reshape(-1, nt)
-    ps2l = torch.stack([pde_instance.partial_s2_log_density_fn(tau[t], xv[:, t, :d]) for t in range(nt)], 0).reshape(-1, nt)
-    c = (ps2l + psl ** 2 + gamma * psl).contiguous()
+    # time derivatives of log rho at every (time stamp, sample): ONE device kernel over coefficient rows cached per
+    # time stamp; the [nt, n] result is then *reshaped* to [n, nt] as the reference does (:57-72, defect D4 kept:
+    # identical for nt == 1)
+    c = pde_instance.density_terms(data.get("tau_0T_host", tau), xv, gamma).reshape(-1, nt)
+    kmv = getattr(pde_instance.cfg, "kmv", None) if hasattr(pde_instance, "cfg") else None
+    m = getattr(kmv, "reference_set_size", None) if kmv is not None else None        # None: m = n (:20-23)
+    closure = bool(getattr(kmv, "moment_closure", False)) if kmv is not None else False
     return ops.kmv_value_and_grad(model, params, flat, xv, c, pde_instance.initial_configuration["tilde_F"],
-                                  common.accumulator_for(model, flat.device), common.result_dict)
+                                  common.accumulator_for(model, flat.device), common.result_dict, m=m, closure=closure)
 
 
 def test_fn(forward_fn, pde_instance, rng):

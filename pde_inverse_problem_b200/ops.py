@@ -1,8 +1,9 @@
-"""Thin tensor-level wrappers over the C ABI (include/pdeip.h).
+"""Thin tensor-level wrappers over the C ABI (include/pdeip.h), dispatched as torch custom ops.
 
 torch supplies device memory and the current CUDA stream; all arithmetic happens inside
-libpdeip.so.  Every wrapper insists on CUDA float32 tensors and raises otherwise — there is no
-CPU or eager fallback.
+libpdeip.so.  The hot-path entry points are registered as `torch.library.custom_op`s (torch_ops.py) and
+called here as `torch.ops.pdeip.*`; the wrappers allocate the outputs (the C ABI never allocates) and
+insist on CUDA float32 tensors — there is no CPU or eager fallback (the ops have no CPU kernel).
 """
 from __future__ import annotations
 
@@ -11,7 +12,11 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
+from . import torch_ops as _T  # noqa: F401  (registers torch.ops.pdeip.*)
 from ._lib import PdeipError  # noqa: F401  (re-export)
+from .torch_ops import as_i64
+
+_ops = torch.ops.pdeip
 
 # count of libpdeip kernel launches issued through this module (bench.py reports it)
 launch_counter = {"n": 0}
@@ -53,7 +58,6 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
     """pdeip_kl_integrate.  z0: [N,2d] (AOS) or [2d,N] (SOA).  Returns (z_last, traj|None, tau|None).
     emit_drift: every trajectory sample is [x, v, grad U(x)] (3d components).
     path: PATH_TENSOR runs the GMM drift contraction on tcgen05 where that kernel exists (see pdeip.h)."""
-    lib = L.load()
     z0 = _f32(z0, "z0")
     if state_layout == L.LAYOUT_AOS:
         n, two_d = z0.shape
@@ -84,12 +88,9 @@ def kl_integrate(z0: torch.Tensor, n_steps: int, dt: float, gamma: float, drift_
         else:
             traj = torch.empty(shape, device=z0.device, dtype=torch.float32)
     tau = torch.empty((n, n_steps), device=z0.device, dtype=torch.float32) if want_tau else None
-    st = lib.pdeip_kl_integrate_path(_ptr(z0), _ptr(z_last), _ptr(traj), _ptr(tau), n, d, n_steps, dt, gamma,
-                                     drift_kind, _ptr(drift_params), n_gaussian, sigma, _ptr(noise), _ptr(tau0),
-                                     seed & 0xFFFFFFFFFFFFFFFF, particle_offset, step_offset, schedule,
-                                     state_layout, traj_layout, emit_every, emit_offset, 1 if emit_drift else 0,
-                                     path, _stream())
-    L.check(st, "pdeip_kl_integrate_path")
+    _ops.kl_integrate(z0, z_last, traj, tau, n, d, n_steps, float(dt), float(gamma), drift_kind, drift_params,
+                      n_gaussian, float(sigma), noise, tau0, as_i64(seed), as_i64(particle_offset), step_offset, schedule,
+                      state_layout, traj_layout, emit_every, emit_offset, 1 if emit_drift else 0, path)
     launch_counter["n"] += 1
     return z_last, traj, tau
 
@@ -129,9 +130,7 @@ def gaussian_sample(n: int, dim: int, mu: Optional[torch.Tensor], cov_half: Opti
     cov_half = _f32(cov_half, "cov_half", allow_none=True)
     shape = (n, dim) if layout == L.LAYOUT_AOS else (dim, n)
     out = torch.empty(shape, device=device, dtype=torch.float32)
-    L.check(L.load().pdeip_gaussian_sample(_ptr(out), n, dim, _ptr(mu), _ptr(cov_half),
-                                           seed & 0xFFFFFFFFFFFFFFFF, particle_offset, layout, _stream()),
-            "pdeip_gaussian_sample")
+    _ops.gaussian_sample(out, n, dim, mu, cov_half, as_i64(seed), as_i64(particle_offset), layout)
     launch_counter["n"] += 1
     return out
 
@@ -176,8 +175,7 @@ def gmm_value_grad(x: torch.Tensor, mus: torch.Tensor, sigma: float = 1.0, want_
         raise PdeipError(f"mus must be [K,{d}], got {tuple(mus.shape)}")
     val = torch.empty((n,), device=x.device, dtype=torch.float32) if want_value else None
     grd = torch.empty_like(x) if want_grad else None
-    L.check(L.load().pdeip_gmm_value_grad(_ptr(x), _ptr(mus), mus.shape[0], float(sigma), _ptr(val), _ptr(grd),
-                                          n, d, _stream()), "pdeip_gmm_value_grad")
+    _ops.gmm_value_grad(x, mus, mus.shape[0], float(sigma), val, grd, n, d)
     launch_counter["n"] += 1
     return val, grd
 
@@ -187,7 +185,7 @@ def linear_grad(x: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
     A = _f32(A, "A")
     n, d = x.shape
     out = torch.empty_like(x)
-    L.check(L.load().pdeip_linear_grad(_ptr(x), _ptr(A), _ptr(out), n, d, _stream()), "pdeip_linear_grad")
+    _ops.linear_grad(x, A, out, n, d)
     launch_counter["n"] += 1
     return out
 
@@ -226,10 +224,8 @@ def model_eval(spec: ModelSpec, params: torch.Tensor, x: torch.Tensor, v: Option
         out["vHv"] = torch.empty((n,), device=x.device, dtype=torch.float32)
     if "laplacian" in want:
         out["laplacian"] = torch.empty((n,), device=x.device, dtype=torch.float32)
-    L.check(L.load().pdeip_model_eval(spec.kind, _ptr(params), spec.d, spec.hidden, spec.layers, spec.n_gaussian,
-                                      _ptr(x), _ptr(v), _ptr(out.get("value")), _ptr(out.get("grad")),
-                                      _ptr(out.get("vHv")), _ptr(out.get("laplacian")), n, _stream()),
-            "pdeip_model_eval")
+    _ops.model_eval(spec.kind, params, spec.d, spec.hidden, spec.layers, spec.n_gaussian, x, v, out.get("value"),
+                    out.get("grad"), out.get("vHv"), out.get("laplacian"), n)
     launch_counter["n"] += 1
     return out
 
@@ -256,8 +252,7 @@ class ResidualAccumulator:
         self.grad = torch.empty((spec.num_params,), device=device, dtype=torch.float32)
 
     def begin(self):
-        L.check(L.load().pdeip_residual_begin(_ptr(self.ws), self.ws_bytes, self.spec.kind, *self.spec.args(),
-                                              _stream()), "pdeip_residual_begin")
+        _ops.residual_begin(self.ws, self.spec.kind, *self.spec.args())
         return self
 
     def accumulate(self, set_kind: int, params: torch.Tensor, points: torch.Tensor, weight: float, coef: float = 0.0,
@@ -285,17 +280,13 @@ class ResidualAccumulator:
                     raise PdeipError(f"points must be [{dim},n], got {tuple(points.shape)}")
                 n_points = points.shape[1]
         tg = true_grad or TrueGrad()
-        L.check(L.load().pdeip_residual_accumulate(
-            _ptr(self.ws), self.ws_bytes, set_kind, self.spec.kind, _ptr(params), *self.spec.args(),
-            _ptr(points), n_points, layout, float(weight), float(coef), tg.kind, _ptr(tg.params), tg.n_gaussian,
-            tg.sigma, path, _stream()), "pdeip_residual_accumulate")
+        _ops.residual_accumulate(self.ws, set_kind, self.spec.kind, params, *self.spec.args(), points, n_points, layout,
+                                 float(weight), float(coef), tg.kind, tg.params, tg.n_gaussian, tg.sigma, path)
         launch_counter["n"] += 1
         return self
 
     def finalize(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        L.check(L.load().pdeip_residual_finalize(_ptr(self.ws), self.ws_bytes, self.spec.kind, *self.spec.args(),
-                                                 _ptr(self.sums), _ptr(self.grad), _stream()),
-                "pdeip_residual_finalize")
+        _ops.residual_finalize(self.ws, self.spec.kind, *self.spec.args(), self.sums, self.grad)
         launch_counter["n"] += 2
         return self.sums, self.grad
 
@@ -313,10 +304,8 @@ def adam_l2_step(params: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: t
             raise PdeipError(f"{name} must be contiguous (updated in place)")
     if norms is None:
         norms = torch.empty((2,), device=params.device, dtype=torch.float32)
-    L.check(L.load().pdeip_adam_l2_step(_ptr(params), _ptr(grad), _ptr(m), _ptr(v), _ptr(ema), params.numel(),
-                                        float(lr), b1, b2, eps, weight_decay, int(count), float(grad_scale),
-                                        1 if use_ema else 0, ema_decay, _ptr(norms), _stream()),
-            "pdeip_adam_l2_step")
+    _ops.adam_l2_step(params, grad, m, v, ema, float(lr), float(b1), float(b2), float(eps), float(weight_decay),
+                      int(count), float(grad_scale), 1 if use_ema else 0, float(ema_decay), norms)
     launch_counter["n"] += 1
     return norms
 
@@ -329,8 +318,7 @@ def ensemble_moments(z: torch.Tensor, layout: int = L.LAYOUT_AOS) -> Tuple[torch
     ws_bytes = int(lib.pdeip_moments_workspace_bytes(dim))
     ws = torch.empty((ws_bytes // 4,), device=z.device, dtype=torch.float32)
     out = torch.empty((dim + dim * dim,), device=z.device, dtype=torch.float32)
-    L.check(lib.pdeip_ensemble_moments(_ptr(z), n, dim, layout, _ptr(out), _ptr(ws), ws_bytes, _stream()),
-            "pdeip_ensemble_moments")
+    _ops.ensemble_moments(z, n, dim, layout, out, ws)
     launch_counter["n"] += 2
     return out[:dim], out[dim:].view(dim, dim)
 
@@ -344,8 +332,7 @@ def gather_0T(dataset: torch.Tensor, sample_index: torch.Tensor, interval: int, 
     n_time_sel = n_time // interval
     n_sel = sample_index.numel()
     out = torch.empty((n_sel * n_time_sel, dim), device=dataset.device, dtype=torch.float32)
-    L.check(L.load().pdeip_gather_0T(_ptr(dataset), n_traj, n_time, dim, _ptr(sample_index.contiguous()), n_sel,
-                                     interval, shift, n_time_sel, _ptr(out), _stream()), "pdeip_gather_0T")
+    _ops.gather_0T(dataset, n_traj, n_time, dim, sample_index.contiguous(), n_sel, interval, shift, n_time_sel, out)
     launch_counter["n"] += 1
     return out
 
@@ -353,41 +340,113 @@ def gather_0T(dataset: torch.Tensor, sample_index: torch.Tensor, interval: int, 
 # ------------------------------------------------------------------------------------------------
 # KMV pairwise residual (kinetic_mckean_vlasov.py:11-120)
 # ------------------------------------------------------------------------------------------------
-def kmv_mean_grad(spec: ModelSpec, params: torch.Tensor, xv: torch.Tensor, true_A: Optional[torch.Tensor] = None):
-    """G[j,t] = mean_i grad Phi(x[j,t] - x[i,t]) and, if true_A is given, the same for Phi_true = D'AD/2.
-    xv: [n, nt, 2d]."""
+def kmv_mean_grad(spec: ModelSpec, params: torch.Tensor, xv: torch.Tensor, true_A: Optional[torch.Tensor] = None,
+                  ref: Optional[torch.Tensor] = None, m: Optional[int] = None):
+    """G[j,t] = mean_i grad Phi(x[j,t] - ref[i,t]) and, if true_A is given, the same for Phi_true = D'AD/2.
+    xv: [n, nt, 2d]; ref: [m, nt, 2d] (None: the batch itself, optionally only its first m trajectories)."""
     params = _f32(params, "params")
     xv = _f32(xv, "xv")
     true_A = _f32(true_A, "true_A", allow_none=True)
+    ref = _f32(ref, "ref", allow_none=True)
     n, nt, two_d = xv.shape
     d = two_d // 2
-    lib = L.load()
-    ws_bytes = int(lib.pdeip_kmv_workspace_bytes(n, nt, d))
+    if ref is None and m is not None and m != n:
+        ref = xv  # sub-sampled reference set: the first m trajectories of the batch
+    m = int(n if ref is None else (ref.shape[0] if m is None else m))
+    ws_bytes = int(L.load().pdeip_kmv_workspace_bytes_ref(n, nt, d, m))
     ws = torch.empty((ws_bytes // 4,), device=xv.device, dtype=torch.float32)
     G = torch.empty((n, nt, d), device=xv.device, dtype=torch.float32)
     Gt = torch.empty_like(G) if true_A is not None else None
-    L.check(lib.pdeip_kmv_mean_grad(spec.kind, _ptr(params), d, spec.hidden, spec.layers, _ptr(xv), n, nt, _ptr(G),
-                                    _ptr(Gt), _ptr(true_A), _ptr(ws), ws_bytes, _stream()), "pdeip_kmv_mean_grad")
+    _ops.kmv_mean_grad(spec.kind, params, d, spec.hidden, spec.layers, xv, n, nt, ref, m, G, Gt, true_A, ws)
     launch_counter["n"] += 2
     return G, Gt
 
 
+def kmv_density_terms(xv: torch.Tensor, coef: torch.Tensor, gamma: float, want_parts: bool = False):
+    """c = d_ss log rho + (d_s log rho)^2 + gamma d_s log rho at every (time stamp, sample) on the device
+    (kinetic_mckean_vlasov_example_quadratic.py:51-69,120-177).  xv [n, nt, 2d]; coef [nt, 3d + 2 + 2d^2]
+    (utils/lyapunov.kmv_density_coefficients).  Returns c as [nt, n] (the reference reshapes it to [n, nt])."""
+    xv = _f32(xv, "xv")
+    coef = _f32(coef, "coef")
+    n, nt, two_d = xv.shape
+    d = two_d // 2
+    if tuple(coef.shape) != (nt, 3 * d + 2 + 2 * d * d):
+        raise PdeipError(f"coef must be [{nt},{3 * d + 2 + 2 * d * d}], got {tuple(coef.shape)}")
+    c = torch.empty((nt, n), device=xv.device, dtype=torch.float32)
+    ps = torch.empty_like(c) if want_parts else None
+    ps2 = torch.empty_like(c) if want_parts else None
+    _ops.kmv_density_terms(xv, n, nt, d, coef, float(gamma), c, ps, ps2)
+    launch_counter["n"] += 1
+    return (c, ps, ps2) if want_parts else c
+
+
 def kmv_value_and_grad(model, params, flat: torch.Tensor, xv: torch.Tensor, c: torch.Tensor, true_A: torch.Tensor,
-                       acc: "ResidualAccumulator", result_dict):
-    """Phase 1 (mean gradient per sample), then the pair set with the extra direction G_j and kappa = 2 c_j."""
+                       acc: "ResidualAccumulator", result_dict, m: Optional[int] = None, closure: bool = False):
+    """Phase 1 (mean gradient per sample), then the pair set with the extra direction G_j and kappa = 2 c_j.
+    m: reference-set size (the first m trajectories of the batch; None = the batch, as the reference).
+    closure: quadratic model only — the pair set against the reference MEAN plus the covariance correction
+    (exactly the full pair set, O(n) instead of O(n m))."""
     xv = _f32(xv, "xv")
     c = _f32(c, "c")
-    n, nt, _ = xv.shape
+    n, nt, two_d = xv.shape
+    d = two_d // 2
     spec = model.spec
-    G, Gt = kmv_mean_grad(spec, flat, xv, true_A)
+    m = n if m is None else int(m)
+    ref, m_eff, cov = None, m, None
+    if closure:
+        if spec.kind != L.MODEL_QUADRATIC:
+            raise PdeipError("the moment closure is exact for the quadratic interaction model only")
+        # per time stamp: mean and covariance of the reference x through the K7 moments kernel
+        ref = torch.zeros((1, nt, two_d), device=xv.device, dtype=torch.float32)
+        cov = torch.empty((nt, d, d), device=xv.device, dtype=torch.float32)
+        for t in range(nt):
+            s1, s2 = ensemble_moments(xv[:m, t, :d].contiguous())
+            mean = s1 / m
+            ref[0, t, :d] = mean
+            cov[t] = s2 / m - torch.outer(mean, mean)
+        m_eff = 1
+    elif m != n:
+        ref = xv
+    G, Gt = kmv_mean_grad(spec, flat, xv, true_A, ref=ref, m=m_eff)
     acc.begin()
-    L.check(L.load().pdeip_residual_accumulate_kmv(_ptr(acc.ws), acc.ws_bytes, spec.kind, _ptr(flat), spec.d,
-                                                   spec.hidden, spec.layers, _ptr(xv), n, nt, _ptr(G), _ptr(Gt),
-                                                   _ptr(c), 1.0 / (float(n) * n * nt), _stream()),
-            "pdeip_residual_accumulate_kmv")
+    w = 1.0 / (float(n) * m_eff * nt)
+    _ops.residual_accumulate_kmv(acc.ws, spec.kind, flat, spec.d, spec.hidden, spec.layers, xv, n, nt, ref, m_eff, G, Gt, c, w)
     launch_counter["n"] += 2
+    if closure:
+        _ops.kmv_closure_correction(acc.ws, flat, d, n, nt, c, cov, w)
+        launch_counter["n"] += 1
     sums, grad = acc.finalize()
     return result_dict(model, params, sums, grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# mean-field drift: the ensemble-mean table of the interacting system (README.md:54-62)
+# ------------------------------------------------------------------------------------------------
+def meanfield_noise_sums(z0: torch.Tensor, n_steps: int, seed: int, particle_offset: int = 0, step_offset: int = 0,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulates into `out` (float64 [(n_steps+1)*d + 2d], zero-initialised if None) the per-step sums of the Philox
+    normals the integrator will draw for these particles, and sum q0, sum p0.  z0: [n, 2d] CUDA."""
+    z0 = _f32(z0, "z0")
+    n, two_d = z0.shape
+    d = two_d // 2
+    if out is None:
+        out = torch.zeros(((n_steps + 1) * d + 2 * d,), device=z0.device, dtype=torch.float64)
+    _ops.meanfield_noise_sums(z0, n, d, n_steps, as_i64(seed), as_i64(particle_offset), step_offset, out)
+    launch_counter["n"] += 1
+    return out
+
+
+def meanfield_drift_params(sums: torch.Tensor, n_global: int, A: torch.Tensor, n_steps: int, dt: float, gamma: float):
+    """(drift_params, xbar): drift_params = [A (d*d) | A xbar_s (n_steps+1, d)] for DRIFT_MEANFIELD_TABLE, xbar
+    [n_steps+1, d] the ensemble mean before every step.  `sums` must already be reduced over ranks."""
+    A = _f32(A, "A")
+    d = A.shape[0]
+    params = torch.empty((d * d + (n_steps + 1) * d,), device=A.device, dtype=torch.float32)
+    params[: d * d] = A.reshape(-1)
+    xbar = torch.empty((n_steps + 1, d), device=A.device, dtype=torch.float32)
+    _ops.meanfield_xbar_table(sums, int(n_global), d, n_steps, float(dt), float(gamma), A, xbar, params[d * d:])
+    launch_counter["n"] += 1
+    return params, xbar
 
 
 def tensor_path_status() -> int:

@@ -154,6 +154,8 @@ class HotPath:
             sums_r, grad_r = parallel.allreduce_sum_packed([sums, grad])
             sums.copy_(sums_r)
             grad.copy_(grad_r)
+            # the norm is not additive over ranks: recompute it from the reduced gradient (common_utils.py:74-76)
+            sums[L.SUM_GRADNORM] = torch.linalg.vector_norm(grad)
         out = {"loss": sums[L.SUM_LOSS], "loss ground truth": sums[L.SUM_GT], "sums": sums, "grad": grad}
         if apply_optimizer and self.optimizer is not None:
             lr = self.optimizer.lr_schedule(self.opt_state.count)
