@@ -11,6 +11,11 @@ terminal states (boundary sets), [all-reduce over ranks], and K6 applies Adam+L2
   value   inputs resident in HBM;   e2e: ensemble in pinned host memory, H2D per chunk and D2H of the loss
           inside the timed region.
 
+Default workload: C5 (BASELINE.json configs[4], the north-star's scaling target): KGMM d=32, K=64, S=200 with
+2^24 particles IN TOTAL, n = 2^24 / world per rank -> "scaling": "strong".  The C3 step (configs[2], 2^22 particles per
+rank) is measured in the same run and reported as `extra.c3`.  C2 / C3 / C4 as --workload keep a fixed ensemble per
+rank ("weak").
+
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5] [--path fp32|tensor]
     python bench.py --impl reference ...     # CPU restatement of the reference (oracle port) on host cores
 """
@@ -39,8 +44,8 @@ WORKLOADS = {
                gamma=0.5, chunk=303104),  # two whole waves of the tcgen05 integrator grid (148 SMs x 8 CTAs x 128 particles)
     "C4": dict(name="KMV-quadratic (-A x drift) d=16 N=2^22 S=100", d=16, K=0, n=1 << 22, S=100, T=2.0,
                gamma=1.0, chunk=1 << 18),
-    "C5": dict(name="KGMM d=32 K=64 N=2^21/rank S=200 (2^24 over 8 ranks)", d=32, K=64, n=1 << 21, S=200, T=2.0,
-               gamma=0.5, chunk=56832),  # 148 SMs x 3 CTAs x 128 particles: one full wave of the tcgen05 integrator
+    "C5": dict(name="KGMM d=32 K=64 N=2^24 total S=200, sharded over the ranks", d=32, K=64, n_total=1 << 24, S=200,
+               T=2.0, gamma=0.5, chunk=56832),  # 148 SMs x 3 CTAs x 128 particles: one full wave of the tcgen05 integrator
 }
 HIDDEN, LAYERS, OUT = 32, 2, 40
 
@@ -56,6 +61,20 @@ def peaks():
             j = json.load(fh)
         return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j["bf16_tflops_sustained"], src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def measured_traffic(kernel_key):
+    """DRAM bytes per residual point of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum / points of the captured launch)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as fh:
+            ent = json.load(fh).get(kernel_key)
+    except (OSError, ValueError):
+        ent = None
+    if not ent:
+        return None, "no ncu --set full capture of %s in profiles/traffic.json" % kernel_key
+    return float(ent["dram_bytes_per_point"]), "profiles/traffic.json[%s] <- %s" % (kernel_key, ent["source"])
 
 
 class ClockSampler:
@@ -136,19 +155,21 @@ def build_problem(w, device, seed=1):
     return drift_kind, drift, true, cov_half, model, params, opt
 
 
-def run_ours(args):
+def measure(name, args, shard, device, local_rank, steps, warmup, with_clocks):
+    """Warm-up + timed steps + e2e + per-kernel phases of one workload on this rank; returns the result dict (rank 0)
+    after the max-over-ranks reduction of the times."""
     from pde_inverse_problem_b200 import _lib as L
-    from pde_inverse_problem_b200 import ops, parallel
+    from pde_inverse_problem_b200 import ops
     from pde_inverse_problem_b200.pipeline import HotPath, HotPathConfig
     import torch.distributed as dist
 
-    shard = parallel.init_from_env("nccl")
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    w = dict(WORKLOADS[args.workload])
+    w = dict(WORKLOADS[name])
+    strong = "n_total" in w and not args.particles
     if args.particles:
         w["n"] = args.particles
+    elif strong:
+        assert w["n_total"] % shard.world == 0
+        w["n"] = w["n_total"] // shard.world
     d, K, n, S = w["d"], w["K"], w["n"], w["S"]
     n_global = n * shard.world
     path = L.PATH_TENSOR if args.path == "tensor" else L.PATH_FP32
@@ -176,25 +197,27 @@ def run_ours(args):
         return t_int, t_res, len(ev)
 
     # ---- warm-up ---------------------------------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         hp.step(z0, seed=100 + i, n_global=n_global, particle_offset=offset)
     barrier()
 
     # ---- timed region: EXACTLY K steps, inputs resident in HBM ---------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if with_clocks else None
+    if sampler:
+        sampler.start()
     ops.launch_counter["n"] = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         out = hp.step(z0, seed=1000 + i, n_global=n_global, particle_offset=offset)
     e1.record()
     barrier()
     launches = ops.launch_counter["n"]
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     t_dev = e0.elapsed_time(e1) / 1e3
     loss = float(out["loss"])
+    assert math.isfinite(loss), "loss is not finite (a timed-out tcgen05 phase poisons it with NaN)"
 
     # ---- e2e: ensemble in pinned host memory, H2D per chunk + D2H of the loss inside the timed region ----
     z0_host = torch.empty((n, 2 * d), dtype=torch.float32, pin_memory=True)
@@ -203,7 +226,7 @@ def run_ours(args):
     hp.step(z0_host, seed=50, n_global=n_global, particle_offset=offset)  # warm the staging path
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(steps, 3))
     f0.record()
     for i in range(e2e_steps):
         o = hp.step(z0_host, seed=2000 + i, n_global=n_global, particle_offset=offset)
@@ -213,6 +236,7 @@ def run_ours(args):
     f1.record()
     barrier()
     t_e2e = f0.elapsed_time(f1) / 1e3
+    del z0_host
 
     # ---- per-kernel phases (separate pass, after the headline timing) ---------------------------------------
     t_int, t_res, n_chunks = timed_phases(seed=3000)
@@ -222,62 +246,90 @@ def run_ours(args):
     if shard.world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_dev, t_e2e, t_int, t_res = [float(x) for x in times]
+    del hp, z0
+    torch.cuda.empty_cache()
+    if shard.rank != 0:
+        return None
 
+    pk = peaks()
+    psteps = n_global * (S + 1)
+    s_emit = S
+    evals = n_global * s_emit
+    # dominant kernel = residual (tensor-pipe roofline, algorithmic 24*M1 FLOP per eval)
+    flop_eval = 24 * m1(d)
+    res_rate = n * s_emit / t_res  # per GPU
+    res_tflops = res_rate * flop_eval / 1e12
+    dp, ns = (8, 2) if d <= 8 else ((16, 1) if d <= 16 else (32, 1))
+    tensor_int = path == L.PATH_TENSOR and K > 0 and d in (8, 16, 32) and K <= 64
+    if path == L.PATH_TENSOR:
+        res_kernel = "tc::mlp_residual_tc_kernel<%d,%d> (KFP 0T set, tcgen05)" % (dp, ns)
+        per_point, res_traffic_src = measured_traffic("mlp_residual_tc<%d,%d>" % (dp, ns))
+    else:
+        res_kernel = "mlp_residual_kernel<32,2,KFP_0T,8> (fp32)"
+        per_point, res_traffic_src = measured_traffic("mlp_residual_fp32")
+    pts_launch = cfg.chunk * s_emit
+    res_traffic = per_point * pts_launch if per_point is not None else None
+    int_rate = n * (S + 1) / t_int
+    int_written = n * s_emit * 3 * d * 4 / t_int / 1e9   # [x, v, grad U(x)] per emitted sample: the bytes really written
+    int_alg = n * s_emit * 2 * d * 4 / t_int / 1e9       # 2d*4 B per emitted particle-step ([x, v])
+    return {
+        "metric": "particle-steps/s", "value": psteps * steps / t_dev, "unit": "particle-steps/s", "n_gpus": shard.world,
+        "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32" if path == L.PATH_FP32 else ("bf16 GEMM operands split hi+lo (MLP weights and x; GMM centres, x and softmax weights "
+                                                  "in the integrator), f32 accumulate / epilogue / state"),
+        "data": "synthetic",
+        "config": {"workload": f"{name}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
+                   "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
+                   "chunk": cfg.chunk, "residual_path": args.path,
+                   "l2_policy": "inputs larger than L2: every chunk's trajectory (%.1f GB) streams through HBM"
+                                % (3 * d * s_emit * cfg.chunk * 4 / 1e9)},
+        "residual_evals_per_s": evals * steps / t_dev,
+        "loss": loss,
+        "e2e": {"value": psteps * e2e_steps / t_e2e, "unit": "particle-steps/s",
+                "h2d_bytes_per_step": n * 2 * d * 4, "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / e2e_steps * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": res_kernel, "bound": "tensor", "achieved": res_tflops,
+                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
+                     "traffic": res_traffic, "traffic_source": res_traffic_src,
+                     "peak_source": pk["src"] + " bf16 sustained",
+                     "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval,
+                     "frac_of_step": (n * s_emit * flop_eval / (t_dev / steps) / 1e12) / pk["tf_sust"]},
+        "kernels": {
+            "kl_integrate": {"kernel": ("kl_integrate_tc_kernel (GMM contraction on tcgen05)" if tensor_int
+                                        else "kl_integrate_fast_kernel (fp32)"), "bound": "hbm",
+                             "achieved": int_written, "peak": pk["hbm"], "unit": "GB/s", "frac": int_written / pk["hbm"],
+                             "bytes_per_emitted_step": 3 * d * 4,
+                             "achieved_algorithmic": int_alg, "frac_algorithmic": int_alg / pk["hbm"],
+                             "algorithmic_bytes_per_emitted_step": 2 * d * 4,
+                             "particle_steps_per_s_per_gpu": int_rate, "ms_per_step": t_int * 1e3},
+            "mlp_residual": {"ms_per_step": t_res * 1e3, "evals_per_s_per_gpu": res_rate},
+        },
+    }
+
+
+def run_ours(args):
+    from pde_inverse_problem_b200 import parallel
+    import torch.distributed as dist
+
+    shard = parallel.init_from_env("nccl")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    line = measure(args.workload, args, shard, device, local_rank, args.steps, args.warmup, with_clocks=True)
+    extra = None
+    if args.workload == "C5" and not args.particles and not args.no_extra:
+        # the C3 step (BASELINE.json configs[2], 2^22 particles per rank) in the same run
+        c3 = measure("C3", args, shard, device, local_rank, steps=max(3, min(args.steps, 5)), warmup=3, with_clocks=False)
+        if c3 is not None:
+            extra = {k: c3[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "residual_evals_per_s", "e2e",
+                                        "roofline", "kernels", "steps", "warmup")}
     if shard.rank == 0:
-        pk = peaks()
-        psteps = n_global * (S + 1)
-        evals = n_global * hp.s_emit
-        ms_step = t_dev / args.steps * 1e3
-        value = psteps * args.steps / t_dev
-        # dominant kernel = residual (tensor-pipe roofline, algorithmic 24*M1 FLOP per eval)
-        flop_eval = 24 * m1(d)
-        res_rate = n * hp.s_emit / t_res  # per GPU
-        res_tflops = res_rate * flop_eval / 1e12
-        # DRAM bytes per residual launch: ncu --set full of this kernel (profiles/r01_summary_tc_integrator.md) measured
-        # 96.6 B per point at d = 8 (96 B algorithmic: x, v, grad U): scaled to this run's points per launch
-        pts_launch = cfg.chunk * hp.s_emit
-        if path == L.PATH_TENSOR and d == 8:
-            res_traffic = 96.6 * pts_launch
-            res_traffic_src = "ncu dram__bytes_read+write per point (151 552-particle capture: 2.927 GB for 30.3 M points) x points per launch"
-        else:
-            res_traffic, res_traffic_src = None, "not captured for this configuration"
-        int_rate = n * (S + 1) / t_int
-        int_gbs = n * hp.s_emit * 3 * d * 4 / t_int / 1e9  # [x, v, grad U(x)] per emitted sample
-        line = {
-            "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": shard.world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if path == L.PATH_FP32 else ("bf16 GEMM operands split hi+lo (MLP weights and x; GMM centres, x and softmax weights "
-                                                      "in the integrator), f32 accumulate / epilogue / state"),
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
-                       "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
-                       "chunk": cfg.chunk, "residual_path": args.path,
-                       "l2_policy": "inputs larger than L2: every chunk's trajectory (%.1f GB) streams through HBM"
-                                    % (hp.traj.numel() * 4 / 1e9)},
-            "residual_evals_per_s": evals * args.steps / t_dev,
-            "loss": loss,
-            "e2e": {"value": psteps * e2e_steps / t_e2e, "unit": "particle-steps/s",
-                    "h2d_bytes_per_step": n * 2 * d * 4, "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / e2e_steps * 1e3},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"kernel": ("tc::mlp_residual_tc_kernel<%d,%d> (KFP 0T set, tcgen05)" % (8 if d <= 8 else (16 if d <= 16 else 32), 2 if d <= 8 else 1)
-                                    if path == L.PATH_TENSOR else "mlp_residual_kernel<32,2,KFP_0T,8> (fp32)"), "bound": "tensor", "achieved": res_tflops,
-                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
-                         "traffic": res_traffic, "traffic_source": res_traffic_src,
-                         "peak_source": pk["src"] + " bf16 sustained",
-                         "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval},
-            "kernels": {
-                "kl_integrate": {"kernel": ("kl_integrate_tc_kernel (GMM contraction on tcgen05)"
-                                            if path == L.PATH_TENSOR and K > 0 and d in (8, 16, 32) and K <= 64
-                                            else "kl_integrate_fast_kernel (fp32)"), "bound": "hbm", "achieved": int_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                                 "frac": int_gbs / pk["hbm"], "particle_steps_per_s_per_gpu": int_rate,
-                                 "bytes_per_emitted_step": 3 * d * 4, "ms_per_step": t_int * 1e3},
-                "mlp_residual": {"ms_per_step": t_res * 1e3, "evals_per_s_per_gpu": res_rate},
-            },
-        }
+        if extra is not None:
+            line["extra"] = {"c3": extra}
         if not args.no_cpu_baseline and shard.world == 1:
-            line["cpu_baseline"] = cpu_baseline(w, seconds_hint=15.0)
+            line["cpu_baseline"] = cpu_baseline(dict(WORKLOADS[args.workload]), seconds_hint=15.0)
         emit_result(line)
     if shard.world > 1:
         dist.barrier()
@@ -348,7 +400,8 @@ def run_reference(args):
               f"oracle port (torch.func restatement; the JAX reference is not installable here)")
     line = {"impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if "n_total" in w else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['name']}", "sample_particles": n_s, "d": w["d"],
                        "n_gaussian": w["K"], "n_steps": w["S"], "mlp": f"{w['d']}->{HIDDEN}x{LAYERS}->{OUT}"},
@@ -383,7 +436,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.c3 block of the default C5 run")
     ap.add_argument("--path", default=os.environ.get("PDEIP_BENCH_PATH", "tensor"), choices=["fp32", "tensor"],
                     help="residual kernel: tensor = tcgen05 bf16 GEMM path (rtol 1e-2, default), fp32 = CUDA-core parity path (rtol 1e-5)")
     ap.add_argument("--particles", type=int, default=0, help="override particles per rank")

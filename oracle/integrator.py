@@ -75,3 +75,41 @@ def fixed_step_scan(z0, n_steps, dt, noise, potential_grad, gamma_friction):
     for s in range(n_steps):
         q, p = update_step(q, p, noise[:, s], dt, potential_grad, gamma_friction)
     return torch.cat([q, p], -1)
+
+
+def interacting_langevin_scan(z0, n_steps, dt, noise, A, gamma_friction):
+    """The interacting particle system of README.md:54-62 with Phi(x) = x'Ax/2: drift grad U = A (x - xbar_t), xbar_t the
+    EMPIRICAL mean of the whole ensemble, recomputed before every step.  The reference never integrates it (it samples
+    the equivalent -A x law, README.md:64-71), so this is the definition the CUDA mean-field table is checked against.
+    Common time grid: utils/sampling_utils.py:32-46 with tau_0 = 0, i.e. step 0 has h = 0 (sample 0 = z0), steps 1..S have
+    h = dt.  Returns (last [N,2d], traj [N,S,2d], xbar [S+1,d] = mean before step s, drift [N,S,d] = grad U at the emitted
+    samples)."""
+    d = z0.shape[1] // 2
+    q, p = z0[:, :d].clone(), z0[:, d:].clone()
+    traj, xbars, drifts = [], [], []
+    for s in range(n_steps + 1):
+        h = 0.0 if s == 0 else dt
+        xbar = q.mean(0)
+        xbars.append(xbar)
+        shift = xbar
+        grad_fn = lambda x: (x - shift) @ A.T
+        if s >= 1:
+            drifts.append(grad_fn(q))
+        q, p = update_step(q, p, noise[:, s], h, grad_fn, gamma_friction)
+        if s < n_steps:
+            traj.append(torch.cat([q, p], -1))
+    return torch.cat([q, p], -1), torch.stack(traj, 1), torch.stack(xbars, 0), torch.stack(drifts, 1)
+
+
+def meanfield_mean_recursion(sum_noise, sum_q0, sum_p0, n_global, dt, gamma_friction):
+    """Closed recursion of the ensemble mean of interacting_langevin_scan: the interaction A (xbar - xbar) vanishes in the
+    mean, so pbar' = (1 - gamma h) pbar + sqrt(2 h) xibar_s, qbar' = qbar + h pbar' with xibar_s = sum_noise[s] / N.
+    sum_noise [S+1, d] (summed over ALL ranks' particles).  Returns xbar [S+1, d] (mean before step s)."""
+    q, p = sum_q0 / n_global, sum_p0 / n_global
+    out = []
+    for s in range(sum_noise.shape[0]):
+        out.append(q.clone())
+        h = 0.0 if s == 0 else dt
+        p = (1.0 - gamma_friction * h) * p + math.sqrt(2.0 * h) * sum_noise[s] / n_global
+        q = q + h * p
+    return torch.stack(out, 0)

@@ -129,8 +129,10 @@ def fp_test_fn(forward_fn, params, data_initial, data_terminal, pde) -> Dict:
     return out
 
 
-def kmv_value_and_grad_fn(forward_fn, params, data: Dict, pde) -> Dict:
-    """kinetic_mckean_vlasov.py:11-120 (pairwise [m,n,n_time,d] residual, m = n)."""
+def kmv_value_and_grad_fn(forward_fn, params, data: Dict, pde, m=None) -> Dict:
+    """kinetic_mckean_vlasov.py:11-120 (pairwise [m,n,n_time,d] residual, m = n).  `m` (not in the reference, which
+    fixes ref_0T = x_0T at :21): use only the first m trajectories as the reference set, the generalisation the
+    commented lines :15-16 (`data["ref"]`) point at."""
     d2 = data["0T"].shape[-1]
     d = d2 // 2
     x_0T, v_0T = data["0T"][:, :d], data["0T"][:, d:]
@@ -138,7 +140,7 @@ def kmv_value_and_grad_fn(forward_fn, params, data: Dict, pde) -> Dict:
     nt = tau_0T.shape[0]
     x_0T = x_0T.reshape(-1, nt, d)  # :19
     v_0T = v_0T.reshape(-1, nt, d)  # :20
-    ref_0T = x_0T  # :21
+    ref_0T = x_0T if m is None else x_0T[:m]  # :21
     x_minus_ref = x_0T[None] - ref_0T[:, None]  # :23  [m,n,nt,d]
     gamma = pde.initial_configuration["gamma_friction"]
 

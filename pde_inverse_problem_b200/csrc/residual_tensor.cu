@@ -1274,6 +1274,16 @@ extern "C" int pdeip_tensor_path_status(void* stream, int* out_status) {
   return pdeip::tensor_path_status((cudaStream_t)stream, out_status);
 }
 
+// test hook: set status word `word` (0 residual, 1 integrator) as a timed-out kernel would
+extern "C" int pdeip_debug_set_status(int word, int value, void* stream) {
+  int* status = pdeip::tensor_status_word();
+  if (!status || word < 0 || word > 1) return PDEIP_ERR_INVALID_ARG;
+  if (cudaMemcpyAsync(status + word, &value, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess)
+    return PDEIP_ERR_CUDA;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return PDEIP_ERR_CUDA;
+  return PDEIP_OK;
+}
+
 // debug (PDEIP_TC_TRACE builds): 24 x 8 clock stamps (see TC_TRACE)
 extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
   int* status = pdeip::tensor_status_word();

@@ -27,7 +27,8 @@ def value_and_grad_fn(forward_fn, params, data, rng, pde_instance, path=None):
     # time stamp; the [nt, n] result is then *reshaped* to [n, nt] as the reference does (:57-72, defect D4 kept:
     # identical for nt == 1)
     c = pde_instance.density_terms(data.get("tau_0T_host", tau), xv, gamma).reshape(-1, nt)
-    kmv = getattr(pde_instance.cfg, "kmv", None) if hasattr(pde_instance, "cfg") else None
+    # pde_instance.kmv.{reference_set_size, moment_closure}: scale options that are not in the reference
+    kmv = getattr(getattr(getattr(pde_instance, "cfg", None), "pde_instance", None), "kmv", None)
     m = getattr(kmv, "reference_set_size", None) if kmv is not None else None        # None: m = n (:20-23)
     closure = bool(getattr(kmv, "moment_closure", False)) if kmv is not None else False
     return ops.kmv_value_and_grad(model, params, flat, xv, c, pde_instance.initial_configuration["tilde_F"],

@@ -84,6 +84,24 @@ class HotPath:
     def residual_evals(self, n: int) -> int:
         return n * self.s_emit
 
+    def meanfield_table(self, z0: torch.Tensor, seed: int, n_global: int, particle_offset: int) -> torch.Tensor:
+        """Interacting system (drift A (x - xbar_t), xbar_t the empirical mean over ALL ranks' particles, README.md:54-62):
+        one pre-pass over the local particles sums the Philox normals of every step (and z0), ONE all-reduce of
+        (S+1) d + 2 d doubles replaces S per-step exchanges of sum x, and the closed recursion of the ensemble mean gives
+        the per-step table the integrator reads (csrc/integrator.cu).  self.drift_params is A [d, d]."""
+        c = self.cfg
+        sums = torch.zeros(((c.n_steps + 1) * c.d + 2 * c.d,), device=self.device, dtype=torch.float64)
+        n = z0.shape[0]
+        for lo in range(0, n, c.chunk):
+            hi = min(n, lo + c.chunk)
+            zc = z0[lo:hi] if z0.is_cuda else self.z_stage[0][: hi - lo].copy_(z0[lo:hi], non_blocking=True)
+            ops.meanfield_noise_sums(zc.contiguous(), c.n_steps, seed, particle_offset=particle_offset + lo, out=sums)
+        if parallel.Shard.current().world > 1:  # float64 sums: not through the float32 packing of allreduce_sum_packed
+            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
+        params, self.xbar = ops.meanfield_drift_params(sums, n_global, self.drift_params, c.n_steps,
+                                                       c.total_time / c.n_steps, c.gamma)
+        return params
+
     def step(self, z0: torch.Tensor, seed: int, n_global: Optional[int] = None, particle_offset: int = 0,
              apply_optimizer: bool = True, phase_events: Optional[list] = None) -> Dict[str, torch.Tensor]:
         """One iteration over the local ensemble z0 [n, 2d] (CUDA, or pinned host memory: then each chunk is
@@ -95,6 +113,9 @@ class HotPath:
         n_global = n if n_global is None else n_global
         dt = c.total_time / c.n_steps
         flat = self.model.flat(self.params)
+        drift_params = self.drift_params
+        if c.drift_kind == L.DRIFT_MEANFIELD_TABLE:
+            drift_params = self.meanfield_table(z0, seed, n_global, particle_offset)
         w_0T = 1.0 / (n_global * self.s_emit)
         w_b = 1.0 / n_global
         self.acc.begin()
@@ -129,7 +150,7 @@ class HotPath:
             if ev:
                 ev[0].record()
             z_last, traj, _ = ops.kl_integrate(
-                zc, c.n_steps, dt, c.gamma, c.drift_kind, self.drift_params, n_gaussian=c.n_gaussian, sigma=c.sigma,
+                zc, c.n_steps, dt, c.gamma, c.drift_kind, drift_params, n_gaussian=c.n_gaussian, sigma=c.sigma,
                 seed=seed, particle_offset=particle_offset + lo,
                 traj_layout=L.TRAJ_BLOCK128 if blocked else L.TRAJ_TIME_SOA,
                 emit_every=c.emit_every, traj_out=self.traj, z_last_out=self.z_last[:nc], emit_drift=True, path=c.path)

@@ -200,3 +200,37 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
                         capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_entry_points_registered_as_torch_custom_ops():
+    """The C ABI is exposed as torch.library.custom_op's (torch.ops.pdeip.*) with mutable-output schemas and NO CPU
+    kernel: a CPU tensor is refused by the dispatcher instead of falling back."""
+    import pytest
+    import torch
+    from pde_inverse_problem_b200 import torch_ops
+    for name in torch_ops.REGISTERED:
+        op = getattr(torch.ops.pdeip, name)
+        schema = str(op.default._schema)
+        assert schema.startswith(f"pdeip::{name}(") and schema.endswith("-> ()") and "!" in schema, schema
+    with pytest.raises(Exception):
+        torch.ops.pdeip.linear_grad(torch.zeros(2, 2), torch.zeros(2, 2), torch.zeros(2, 2), 2, 2)
+    assert torch_ops.as_i64(2 ** 64 - 1) == -1 and torch_ops._u64(-1) == 2 ** 64 - 1
+
+
+def test_v_hypothesis_envelope_and_padding_layout():
+    """hidden_dim <= 32 is zero-padded into the 32-wide kernels; wider / deeper / mixed networks fail with a message that
+    names the supported envelope (the reference default MLP.yaml is hidden_dim 20, layers 8)."""
+    import pytest
+    import torch
+    from pde_inverse_problem_b200.core.model import V_hypothesis
+    m = V_hypothesis(1, [20] * 8, 4)
+    assert m.spec.hidden == 32 and m.spec.layers == 8
+    assert m.spec.num_params == 4 * 32 + 32 + 7 * (32 * 32 + 32) + 32 * 40 + 40
+    tree = m.tree(torch.arange(m.spec.num_params, dtype=torch.float32))
+    assert tuple(tree["params"]["layers_0"]["kernel"].shape) == (4, 20)
+    assert tuple(tree["params"]["layers_3"]["kernel"].shape) == (20, 20)
+    assert tuple(tree["params"]["layers_8"]["kernel"].shape) == (20, 40)
+    assert tree["params"]["layers_1"]["kernel"][1, 2].item() == 4 * 32 + 32 + 1 * 32 + 2  # a view of the padded buffer
+    for bad in ([64, 64], [32] * 9, [16, 32]):
+        with pytest.raises(NotImplementedError, match="hidden"):
+            V_hypothesis(1, bad, 4)

@@ -116,9 +116,10 @@ def test_kmv_pairwise_residual(cuda, model_kind, d, nt):
                                  c.float().contiguous().to(cuda), pde.initial_configuration["tilde_F"].float().to(cuda),
                                  acc, lambda m_, p_, s, gr: (s.cpu().double(), gr.cpu().double()))
     sums, gflat = out
-    assert relmax(sums[L.SUM_LOSS], ref["loss"]) < 2e-5
-    assert relmax(sums[L.SUM_GT], ref["loss ground truth"]) < 2e-5
-    assert relmax(gflat, o_model.flatten_params(ref["grad"])) < 2e-5
+    e = (relmax(sums[L.SUM_LOSS], ref["loss"]), relmax(sums[L.SUM_GT], ref["loss ground truth"]),
+         relmax(gflat, o_model.flatten_params(ref["grad"])))
+    print(f"KMV {model_kind} d={d} nt={nt}: loss {e[0]:.2e} gt {e[1]:.2e} grad {e[2]:.2e}")
+    assert max(e) < TOL, e
 
 
 def test_exact_samplers_reproduce_analytic_moments(cuda):
@@ -181,6 +182,14 @@ def _cfg(pde, **kw):
     ("OU-FP online exact, MLP", "fokker_planck",
      {"estimation_mode": "non-parametric", "pde_instance.total_evolving_time": 5.0, "solver.train.batch_size_0T": 3000,
       "solver.train.batch_size_init": 3000, "solver.train.batch_size_terminal": 3000}),
+    ("KOU online exact, MLP with the reference's default network (hidden_dim 20, layers 8: MLP.yaml)",
+     "kinetic_fokker_planck",
+     {"estimation_mode": "non-parametric", "neural_network.hidden_dim": 20, "neural_network.layers": 8,
+      "solver.train.batch_size_0T": 2000, "solver.train.batch_size_init": 1000, "solver.train.batch_size_terminal": 1000}),
+    ("KMV online, parametric, moment closure", "kinetic_mckean_vlasov",
+     {"estimation_mode": "parametric", "pde_instance.domain_dim": 2, "solver.train.sample_mode": "grid_time",
+      "solver.train.n_time_stamps": 1, "solver.train.sample_per_time": 3000, "solver.train.batch_size_init": 100,
+      "solver.train.batch_size_terminal": 100, "pde_instance.kmv": {"moment_closure": True}}),
     ("KMV online, parametric", "kinetic_mckean_vlasov",
      {"estimation_mode": "parametric", "pde_instance.domain_dim": 2, "solver.train.sample_mode": "grid_time",
       "solver.train.n_time_stamps": 1, "solver.train.sample_per_time": 300, "solver.train.batch_size_init": 100,

@@ -63,7 +63,7 @@ def test_tensor_path_matches_oracle(cuda, d, n):
     off = 0
     for w_, b_ in zip(dW, db):
         for leaf in (w_, b_):
-            assert relmax(gr[off:off + leaf.numel()], leaf.reshape(-1)) < 2 * TOL
+            assert relmax(gr[off:off + leaf.numel()], leaf.reshape(-1)) < TOL, (d, n, off)
             off += leaf.numel()
 
 
@@ -132,7 +132,7 @@ def test_tensor_path_edge_sizes(cuda, n):
         assert float(stc.abs().sum()) == 0.0 and float(gtc.abs().sum()) == 0.0
         return
     assert relmax(stc[L.SUM_LOSS], s32[L.SUM_LOSS]) < TOL
-    assert relmax(gtc, g32) < 2 * TOL
+    assert relmax(gtc, g32) < TOL
 
 
 @pytest.mark.parametrize("path_name,d", [("fp32", 8), ("tensor", 8), ("tensor", 32), ("fp32", 16)])

@@ -73,3 +73,55 @@ def test_sharded_residual_allreduce_world2():
     rg = o_model.flatten_params(ref["grad"])
     assert ((flat_r - rg).abs().max() / rg.abs().max()).item() < 1e-5
     assert mx.item() == pytest.approx(0.5) and torch.allclose(mg, torch.full((5,), 1.0))
+
+
+def _meanfield_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import numpy as np
+    from oracle import philox as o_philox
+    from pde_inverse_problem_b200 import parallel
+    shard = parallel.init_from_env("gloo")
+    n, d, S, seed = 600, 3, 12, 99
+    g = torch.Generator().manual_seed(1)
+    z0 = torch.randn(n, 2 * d, generator=g, dtype=torch.float64) + 0.5
+    lo, hi = shard.bounds(n)
+    ids = np.arange(lo, hi)
+    # what pdeip_meanfield_noise_sums accumulates on each rank: per-step sums of the Philox normals keyed by the GLOBAL
+    # particle id, then sum q0, sum p0 — float64, reduced with ONE all-reduce (pipeline.HotPath.meanfield_table)
+    sums = torch.zeros((S + 1) * d + 2 * d, dtype=torch.float64)
+    for s in range(S + 1):
+        sums[s * d:(s + 1) * d] = torch.as_tensor(o_philox.normals(seed, ids, s, d).sum(0))
+    sums[(S + 1) * d:(S + 1) * d + d] = z0[lo:hi, :d].sum(0)
+    sums[(S + 1) * d + d:] = z0[lo:hi, d:].sum(0)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(sums)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_meanfield_noise_sums_shard_and_close_world2():
+    """The mean-field drift needs no per-step exchange: per-rank noise sums + ONE float64 all-reduce + the closed mean
+    recursion reproduce the per-step empirical mean of the full interacting ensemble (rank-count invariant)."""
+    import numpy as np
+    from oracle import integrator as o_int, philox as o_philox
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_meanfield_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    sums = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    n, d, S, seed, dt, gamma = 600, 3, 12, 99, 0.05, 1.0
+    g = torch.Generator().manual_seed(1)
+    z0 = torch.randn(n, 2 * d, generator=g, dtype=torch.float64) + 0.5
+    noise = torch.as_tensor(np.stack([o_philox.normals(seed, np.arange(n), s, d) for s in range(S + 1)], 1))
+    A = torch.tensor([[2.0, 0.3, 0.0], [0.3, 1.5, 0.2], [0.0, 0.2, 1.0]], dtype=torch.float64)
+    _, _, xbars, _ = o_int.interacting_langevin_scan(z0, S, dt, noise, A, gamma)
+    xb = o_int.meanfield_mean_recursion(sums[: (S + 1) * d].view(S + 1, d), sums[(S + 1) * d:(S + 1) * d + d],
+                                        sums[(S + 1) * d + d:], n, dt, gamma)
+    assert (xb - xbars).abs().max().item() < 1e-12

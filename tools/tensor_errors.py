@@ -19,11 +19,13 @@ for d, n, seed in [(8, 20000, 3), (16, 5000, 7), (4, 5000, 5), (32, 3000, 11), (
     s, gr = acc.finalize()
     s, gr = s.double().cpu(), gr.double().cpu()
     ref = torch.cat([torch.cat([w_.reshape(-1), b_.reshape(-1)]) for w_, b_ in zip(r["dW"], r["db"])])
-    off, worst = 0, 0.0
-    for w_, b_ in zip(r["dW"], r["db"]):
-        for leaf in (w_, b_):
+    off, worst, per_leaf = 0, 0.0, []
+    for li, (w_, b_) in enumerate(zip(r["dW"], r["db"])):
+        for nm, leaf in (("W", w_), ("b", b_)):
             k = leaf.numel()
-            worst = max(worst, ((gr[off:off + k] - leaf.reshape(-1)).abs().max() / leaf.abs().max()).item())
+            e = ((gr[off:off + k] - leaf.reshape(-1)).abs().max() / leaf.abs().max()).item()
+            per_leaf.append(f"{nm}{li} {e:.1e} (|leaf| {leaf.abs().max().item():.1e})")
+            worst = max(worst, e)
             off += k
     print(f"d={d:2d} n={n:5d}: loss {abs(float(s[L.SUM_LOSS]) - float(r['loss'])) / abs(float(r['loss'])):.1e} "
-          f"grad {((gr - ref).abs().max() / ref.abs().max()).item():.1e} worst-leaf {worst:.1e}")
+          f"grad {((gr - ref).abs().max() / ref.abs().max()).item():.1e} worst-leaf {worst:.1e}   " + "  ".join(per_leaf))
