@@ -208,8 +208,8 @@ int pdeip_residual_begin(void* workspace, size_t workspace_bytes, int model_kind
  * true_kind/true_params/true_n_gaussian/true_sigma: drift spec (PDEIP_DRIFT_LINEAR / _GMM / _NONE) of
  *   grad V_true, used by the *_0T kinds for sum|gV_true|^2 and "loss ground truth"; PDEIP_DRIFT_IN_POINTS: the points
  *   carry d extra components holding grad V_true (rows of dim + d floats / dim + d planes).
- * path: PDEIP_PATH_FP32 or PDEIP_PATH_TENSOR (MLP model 32 x 2; KFP_0T and FP_0T run on tcgen05 — FP_0T as d + 1
- *   direction rows (x, e_i | 0) per point stacked along the GEMM M dimension —, the boundary kinds stay fp32). */
+ * path: PDEIP_PATH_FP32 or PDEIP_PATH_TENSOR (MLP model 32 x 2; KFP_0T and FP_0T run on tcgen05 — FP_0T as d
+ *   direction rows (x, e_i) per point stacked along the GEMM M dimension —, the boundary kinds stay fp32). */
 int pdeip_residual_accumulate(void* workspace, size_t workspace_bytes, int set_kind, int model_kind,
                               const float* params, int d, int hidden, int layers, int n_gaussian,
                               const float* points, int64_t n_points, int layout, float weight, float coef,

@@ -44,7 +44,7 @@ struct ResidualArgs {
   const float* ref;
   int64_t kmv_n;
   int kmv_nt;
-  // tensor path, FP 0T set: fp_dirs = d + 1 virtual (x, direction) rows per point (0: kinetic point set)
+  // tensor path, FP 0T set: fp_dirs = d direction tiles (x, e_i) per point tile (0: kinetic point set)
   int fp_dirs;
 };
 

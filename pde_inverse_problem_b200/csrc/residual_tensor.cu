@@ -28,13 +28,13 @@
 //   parity  rtol 1e-2 (BASELINE.json, bf16 GEMM path); measured against the oracle in tests/test_gpu_tensor.py.
 //
 // FP 0T set (methods/consistency_instances/fokker_planck.py:33-63: |g|^2 - 2 sum_i D_{e_i}^2 V, the d forward-mode
-// tangents of jacfwd(grad V)) on the same kernel: the d tangent streams e_1..e_d of a point are STACKED ALONG M as d
-// rows (x, v = e_i) of the tile, plus one row (x, v = 0) of weight -(d - 1).  With gamma = 0 a row contributes
-// l(x, v) = |g|^2 - 2 D_v^2 V, so  sum_i l(x, e_i) - (d - 1) l(x, 0) = |g|^2 - 2 Laplacian V  and the same combination
-// of the parameter gradients (every per-row quantity is linear in the row weight `mk`).  The |g|^2 parts cancel
-// exactly: rows of the same x run the same instructions on the same operands.  a.fp_dirs = d + 1 virtual rows per
-// point; row p is (point p / (d+1), direction p % (d+1)).  Cost: (d + 1) KFP evaluations per point (the primal and
-// the g-stream are recomputed per direction: 2x the algorithmic FLOPs of a shared-primal kernel).
+// tangents of jacfwd(grad V)) on the same kernel: the d tangent streams e_1..e_d of a point are STACKED ALONG M, one
+// tile row (x, v = e_i) per direction, with gamma = 0 and the |g|^2 coefficient c_g = 1/d per row, so that the rows of a
+// point add up to  sum_i (|g|^2 / d - 2 D_{e_i}^2 V) = |g|^2 - 2 Laplacian V  (and the same for the parameter gradient;
+// the g-stream is linear in its direction, so c_g enters once, as the direction c_g g / 2 written in E6).  a.fp_dirs = d: virtual tile T is
+// (point tile T / d, direction T % d): the d tiles of one point tile are consecutive (its inputs stay in L1 / L2) and
+// every row of a tile has the same direction.  Cost: d KFP evaluations per point (the primal, the input-gradient chain
+// and the g-stream are recomputed per direction: ~2x the executed FLOPs of a shared-primal kernel).
 #include "mlp_thread.cuh"
 #include "residual_common.cuh"
 #include "umma.cuh"
@@ -400,8 +400,17 @@ __device__ __forceinline__ void st2(float* v, int i, float2 x) { v[2 * i] = x.x;
 __device__ __forceinline__ float2 unp2(const uint32_t* r, int i) { return make_float2(bf_lo(r[i]), bf_hi(r[i])); }
 __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
 
-template <int DP, int NS>
+// BND: the KFP boundary sets (kinetic_fokker_planck.py:34-39,48-50: l = coef grad V . v, coef = +-2/T) on the same phase
+// schedule with the seeds of that loss (alpha = 0, beta = coef, no |g|^2 term: za^ = 0, so the input-gradient chain, the
+// g-stream and the c chains carry zeros) and the lo weight halves on EVERY stream: mean D_v V over a boundary set is a
+// heavily cancelling sum, and the systematic part of the bf16 weight rounding (the same for every point, it does not
+// average out) showed at 1.1e-2 in that term with hi-only tangent streams (profiles/r01_summary_tensor_v2.md item 7).
+// MODE: 0 KFP 0T set, 1 KFP boundary set (BND), 2 FP 0T set as direction tiles (FPM) — compile-time, so that the 0T kernel
+// carries none of the other modes' code (the epilogue is instruction-fetch sensitive).
+constexpr int kModeKfp0T = 0, kModeBnd = 1, kModeFp0T = 2;
+template <int DP, int NS, int MODE>
 __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
+  constexpr bool BND = MODE == kModeBnd, FPM = MODE == kModeFp0T;
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -420,9 +429,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   // Every CTA owns a CONTIGUOUS range of tiles (a multiple of NS): its input stream walks one region of the point set
   // front to back (one new 2 MB page every ~170 tiles at d = 8 instead of every tile with a grid-strided assignment).
   // n_tiles is the END of this CTA's range.
-  const int fpd = a.fp_dirs;                                                   // 0: kinetic rows (x, v)
-  const int64_t n_rows = fpd ? a.n_points * fpd : a.n_points;                 // (virtual) rows of this point set
-  const int64_t n_tiles_all = (n_rows + 127) / 128;
+  const uint32_t fpd = FPM ? (uint32_t)a.fp_dirs : 1u;                         // FP: d direction tiles per point tile
+  const int64_t n_tiles_all = (a.n_points + 127) / 128 * fpd;                  // (virtual) tiles of this point set
   const int64_t per_cta = ((n_tiles_all + gridDim.x - 1) / gridDim.x + NS - 1) / NS * NS;
   const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
   if (tile_begin >= n_tiles_all) return;  // nothing to do for this CTA (uniform)
@@ -507,6 +515,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // only: with one slot a chain in front of the next layer GEMM is fully exposed (d = 32: -2.5 %) — c_1^T za1 behind
     // P7's and c_2^T za2 behind P8's.  d = 8: 2.98e9 -> 3.01e9 evals/s.
     constexpr bool kCChainsEarly = PDEIP_TC_G_CHAIN_EARLY && NS == 2;
+    constexpr int kNloFwd = BND ? 2 : PDEIP_TC_NLO_FWD;  // BND: primal and order-1 streams get the lo halves
+    constexpr int kNloBwd = BND ? 2 : PDEIP_TC_NLO_BWD;
     // NOTE: a compact switch over the phase (about 13 KB of code) measured FASTER than the fully written-out sequence
     // (26 KB): the epilogue warps are instruction-fetch sensitive and the larger MMA stream evicts their code.
     // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
@@ -530,23 +540,23 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
             switch (ph) {
               case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
                 mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
-                mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
+                mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
                 commit(mb);
               } break;
               case 1: {  // z1, z1_1, z2^_1
-                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD, PDEIP_TC_NLO_FWD>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
+                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
               case 2: {  // u, u1, u2^
-                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD, PDEIP_TC_NLO_FWD>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
+                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
               case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
-                mm_bwd<OP, 32, 2, true, PDEIP_TC_NLO_BWD>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
+                mm_bwd<OP, 32, 2, true, kNloBwd>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
               } break;
               case 4: {  // aa1 = za1 W1^T, ab1_1 = zbar1' W1^T;  dW1 += a1_1^T zbar1'
-                mm_bwd<32, 32, 2, true, PDEIP_TC_NLO_BWD>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
+                mm_bwd<32, 32, 2, true, kNloBwd>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
               } break;
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
@@ -579,11 +589,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 }
               } break;
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
-                mm_bwd<OP, 32, 2, false>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                mm_bwd<OP, 32, 2, BND, 1>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
               } break;
               case 10: {  // ab_1 = zbar0' W1^T, aa1 again;  dW1 += t1^T zbar0' + c_1^T za1
-                mm_bwd<32, 32, 2, false>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                mm_bwd<32, 32, 2, BND, 1>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
               } break;
               default: {  // dW0 += x_hi^T zbar0'' (+ x_lo^T zbar0'' if PDEIP_TC_XLO_DW) + g^^T za0
@@ -657,7 +667,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     for (int i = 0; i < 24; ++i) db2[i] = 0.f;
     float sum_g2 = 0.f, sum_gt2 = 0.f, sum_gd2 = 0.f, sum_d1 = 0.f, sum_d2 = 0.f;
     const float gamma = a.coef, gamma4 = 4.f * a.coef;
-    const int dimw = (fpd ? d : 2 * d) + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
+    const float cgw = 1.f / (float)fpd;  // coefficient of the |g|^2 term per row (FP: 1/d per direction row; else 1)
+    const int dimw = (FPM ? d : 2 * d) + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? d : 0);  // floats per point
     // byte offsets of this thread's row inside the operand tiles (chunk c adds c * 128)
     const uint32_t offX = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_X;
     const uint32_t offA = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_A;
@@ -669,10 +680,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     float xin0[NI][8], xin1[NI][8];
     auto load_into = [&](float (&xin)[NI][8], int64_t t) {
       const int64_t cstride = comp_stride(a.layout, a.n_points);
-      const int64_t pp = t * 128 + row;
-      const int64_t pr = (t < n_tiles && pp < n_rows) ? pp : 0;
-      const int64_t pc = fpd ? pr / fpd : pr;                 // FP: row -> (point, direction)
-      const int dir = fpd ? (int)(pr - pc * fpd) : -1;
+      // FP: virtual tile -> (point tile, direction); tile counts stay below 2^31
+      const uint32_t tq = FPM ? (uint32_t)t / fpd : 0u;
+      const int dir = FPM ? (int)((uint32_t)t - tq * fpd) : -1;
+      const int64_t pp = (FPM ? (int64_t)tq : t) * 128 + row;
+      const int64_t pc = (t < n_tiles && pp < a.n_points) ? pp : 0;
       const float* const pbase = a.points + point_base(a.layout, pc, dimw);
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -680,13 +692,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const int band = (j / S::XC) < 3 ? (j / S::XC) : 0, cg = j % S::XC;
         const int bandc = (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS) ? band : 0;
         // FP rows hold [x (d), grad V_true (d, IN_POINTS)]: the gt band sits right after x, the v band is e_dir
-        const int bandm = fpd ? (bandc == 2 ? 1 : 0) : bandc;
+        const int bandm = FPM ? (bandc == 2 ? 1 : 0) : bandc;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int u = cg * 8 + e;
           const int uc = u < d ? u : 0;
           const float val = __ldg(pbase + (bandm * d + uc) * cstride);
-          xin[i][e] = (fpd && band == 1) ? (u == dir ? 1.f : 0.f) : val;
+          xin[i][e] = (FPM && band == 1) ? (u == dir ? 1.f : 0.f) : val;
         }
       }
     };
@@ -704,7 +716,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // destination register, nothing to wait for; prefetch.global.L2 = CCTL.PF2 measured ~700 cycles per phase) and E0
     // issues the loads itself, before its commit wait: they hit L2 and land behind that wait.
     auto prefetch_inputs = [&](int64_t t) {
-      if (fpd || t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // FP rows / ragged last tile: not worth a special case
+      if (FPM || t >= n_tiles || (t + 1) * 128 > a.n_points) return;  // FP tiles / ragged last tile: not worth a special case
       if (a.layout == PDEIP_LAYOUT_SOA) {  // dimw component segments of 512 B
         if ((a.n_points & 3) == 0 && half == 0 && row < dimw)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.points + (int64_t)row * a.n_points + t * 128),
@@ -735,11 +747,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z + offZ;
       const uint32_t LA = LA0 + (uint32_t)s * SLOT_COLS;
       const int64_t tile = base + s;
-      const int64_t prow = tile * 128 + row;
-      const bool valid = tile < n_tiles && prow < n_rows;
-      const int64_t p = fpd ? prow / fpd : prow;  // point index of this row
-      // row weight: 1, or for the FP direction rows  +1 (v = e_i) / -(d - 1) (v = 0)
-      const float mk = !valid ? 0.f : ((fpd && prow - p * fpd == fpd - 1) ? -(float)(fpd - 2) : 1.f);
+      const int64_t p = (FPM ? (int64_t)((uint32_t)tile / fpd) : tile) * 128 + row;  // point of this thread's row
+      const bool valid = tile < n_tiles && p < a.n_points;
+      const float mk = valid ? 1.f : 0.f;
 #ifdef PDEIP_TC_PROBE
       const bool probe_on = blockIdx.x == 0 && tile == 0;
 #endif
@@ -851,7 +861,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         for (int i = 0; i < 6; ++i)
           *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(bias_s + 64 + u24 + 4 * i);
         tm_wait_ld();
-        const float k8 = 8.f * mk, kg = gamma4 * mk;
+        // seeds of l = alpha D_v^2 V + beta D_v V (+ |g|^2):  0T set alpha = -2, beta = 2 gamma;  BND alpha = 0, beta = coef
+        const float k8 = BND ? 0.f : 8.f * mk, kg = (BND ? 2.f * a.coef : gamma4) * mk;
         float d1 = 0.f, d2a = 0.f, d2b = 0.f;
         float za[24], sv[24], sp[24];
 #if PDEIP_TC_PACKED
@@ -957,21 +968,20 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
             float g4[8], gv[8], gt[8];
             tm_ld8(LA + C_G + 8 * cg, reinterpret_cast<uint32_t*>(g4));
             tm_wait_ld();
-            // the chain za^ carries the row weight mk (it seeds the adjoints): g itself is weight-free
-            const float gsc = mk != 0.f ? 0.25f / mk : 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              gv[e] = gsc * g4[e];
+              gv[e] = 0.25f * g4[e];
               gt[e] = 0.f;
             }
             if (band == 0) {
               float gh[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) gh[e] = 0.5f * gv[e];
+              for (int e = 0; e < 8; ++e) gh[e] = (0.125f * cgw) * g4[e];  // the g-stream is linear in its direction: c_g g / 2
               put_chunk(X, (S::XC_G + cg) * 128, gh);
               TC_PROBE(15, cg * 8, gv, 8);
             }
             if (own_sum) {
+              const float mkc = mk * cgw;  // FP: each of the d direction rows of a point carries 1/d of the per-point sums
               if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) gt[e] = (valid && cg * 8 + e < d) ? ((NS == 2 && s == 1) ? xin1[i][e] : xin0[i][e]) : 0.f;
@@ -981,9 +991,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float df = gt[e] - gv[e];
-                sum_g2 = fmaf(mk * gv[e], gv[e], sum_g2);
-                sum_gt2 = fmaf(mk * gt[e], gt[e], sum_gt2);
-                sum_gd2 = fmaf(mk * df, df, sum_gd2);
+                sum_g2 = fmaf(mkc * gv[e], gv[e], sum_g2);
+                sum_gt2 = fmaf(mkc * gt[e], gt[e], sum_gt2);
+                sum_gd2 = fmaf(mkc * df, df, sum_gd2);
               }
             }
           }
@@ -1023,7 +1033,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
         TC_PROBE(l1 ? 16 : 17, u16, cc, 16);
       } else if constexpr (ph == 9) {
-        // E9: s0 = s0p + 8 mk ug^;  db2 += s0
+        // E9: s0 = s0p + 8 ug^;  db2 += s0
         float ug[24], s0[24];
         uint32_t spp[12];
         tm_ldp<24>(LA + C_S0P + 12 * half, spp);
@@ -1034,14 +1044,14 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #if PDEIP_TC_PACKED
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-          const float2 v = __ffma2_rn(bc2(8.f * mk), pr(ug, i), unp2(spp, i));  // the g-stream is weight-free: weight its seed
+          const float2 v = __ffma2_rn(bc2(8.f), pr(ug, i), unp2(spp, i));
           st2(s0, i, v);
           st2(db2, i, __fadd2_rn(pr(db2, i), v));
         }
 #else
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
-          s0[i] = fmaf(8.f * mk, ug[i], unp(spp, i));
+          s0[i] = fmaf(8.f, ug[i], unp(spp, i));
           db2[i] += s0[i];
         }
 #endif
@@ -1191,12 +1201,17 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         for (int w = 0; w < kEpiThreads / 32; ++w)
           for (int k = 0; k < 5; ++k) t5[k] += red[512 + w * 8 + k];
         const float g2 = wt * t5[0], gt2 = wt * t5[1], gd2 = wt * t5[2], D1 = wt * t5[3], D2 = wt * t5[4];
-        part[P + PDEIP_SUM_G2] += g2;
-        part[P + PDEIP_SUM_GTRUE2] += gt2;
-        part[P + PDEIP_SUM_GT] += gd2;
-        if (!fpd) part[P + PDEIP_SUM_D1] += D1;  // FP rows: D_{e_i} V is not a loss term (fokker_planck.py:50-51)
-        part[P + PDEIP_SUM_D2] += D2;
-        part[P + PDEIP_SUM_LOSS] += g2 + gt2 - 2.f * D2 + 2.f * gamma * D1;
+        if constexpr (BND) {  // residual_mlp.cu, KFP_BOUNDARY: sum coef grad V . v
+          part[P + PDEIP_SUM_BOUNDARY] += a.coef * D1;
+          part[P + PDEIP_SUM_LOSS] += a.coef * D1;
+        } else {
+          part[P + PDEIP_SUM_G2] += g2;
+          part[P + PDEIP_SUM_GTRUE2] += gt2;
+          part[P + PDEIP_SUM_GT] += gd2;
+          if (!FPM) part[P + PDEIP_SUM_D1] += D1;  // FP rows: D_{e_i} V is not a loss term (fokker_planck.py:50-51)
+          part[P + PDEIP_SUM_D2] += D2;
+          part[P + PDEIP_SUM_LOSS] += g2 + gt2 - 2.f * D2 + 2.f * gamma * D1;
+        }
       }
     }
   }
@@ -1222,10 +1237,10 @@ int* tensor_status_word() {
 }
 
 #ifdef PDEIP_HAVE_TENSOR_PATH
-template <int DP, int NS>
+template <int DP, int NS, int MODE>
 static int launch_tc(const ResidualArgs& a, int* status, cudaStream_t st) {
   using S = tc::Cfg<DP, NS>;
-  auto kern = tc::mlp_residual_tc_kernel<DP, NS>;
+  auto kern = tc::mlp_residual_tc_kernel<DP, NS, MODE>;
   PDEIP_REQUIRE(true_grad_floats(a.tg, a.d) * sizeof(float) <= S::TP_BYTES, PDEIP_ERR_UNSUPPORTED,
                 "tensor path: true-gradient parameters exceed %u bytes", (unsigned)S::TP_BYTES);
   PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
@@ -1235,22 +1250,34 @@ static int launch_tc(const ResidualArgs& a, int* status, cudaStream_t st) {
 }
 
 int mlp_residual_accumulate_tensor(int set_kind, const ResidualArgs& a, int hidden, cudaStream_t st) {
-  // boundary sets (two launches over n points vs n*S points of the 0T set) stay on the fp32 kernel
-  if (set_kind != PDEIP_SET_KFP_0T && set_kind != PDEIP_SET_FP_0T) return mlp_residual_accumulate_fp32(set_kind, a, hidden, st);
-  if (set_kind == PDEIP_SET_FP_0T) {  // d tangent streams stacked along M: d + 1 rows (x, e_i | 0) per point, gamma = 0
-    ResidualArgs f = a;
-    f.fp_dirs = a.d + 1;
-    f.coef = 0.f;
-    return mlp_residual_accumulate_tensor(PDEIP_SET_KFP_0T, f, hidden, st);
-  }
+  // FP boundary (coef V) and KMV pairs stay on the fp32 kernel
+  if (set_kind != PDEIP_SET_KFP_0T && set_kind != PDEIP_SET_FP_0T && set_kind != PDEIP_SET_KFP_BOUNDARY)
+    return mlp_residual_accumulate_fp32(set_kind, a, hidden, st);
   PDEIP_REQUIRE(hidden == 32 && a.layers == 2, PDEIP_ERR_UNSUPPORTED,
                 "tensor path is built for hidden_dim == 32, layers == 2 (got %d, %d)", hidden, a.layers);
   PDEIP_REQUIRE(a.d >= 1 && a.d <= 32, PDEIP_ERR_UNSUPPORTED, "tensor path supports 1 <= d <= 32 (got %d)", a.d);
   int* status = tensor_status_word();
   PDEIP_REQUIRE(status != nullptr, PDEIP_ERR_CUDA, "cannot allocate the tensor-path status word");
-  if (a.d <= 8) return launch_tc<8, 2>(a, status, st);
-  if (a.d <= 16) return launch_tc<16, 1>(a, status, st);
-  return launch_tc<32, 1>(a, status, st);
+  ResidualArgs b = a;
+  int mode = tc::kModeKfp0T;
+  if (set_kind == PDEIP_SET_FP_0T) {  // d tangent streams stacked along M: one tile row (x, e_i) per direction, gamma = 0
+    PDEIP_REQUIRE((a.n_points + 127) / 128 * (int64_t)a.d < ((int64_t)1 << 31), PDEIP_ERR_UNSUPPORTED,
+                  "FP tensor path: n_points * d / 128 must stay below 2^31");
+    b.fp_dirs = a.d;
+    b.coef = 0.f;
+    mode = tc::kModeFp0T;
+  } else if (set_kind == PDEIP_SET_KFP_BOUNDARY) {
+    b.tg.kind = PDEIP_DRIFT_NONE;  // boundary points are rows [x, v]
+    mode = tc::kModeBnd;
+  }
+#define PDEIP_TC_DISPATCH(DP, NS)                                                     \
+  (mode == tc::kModeKfp0T ? launch_tc<DP, NS, tc::kModeKfp0T>(b, status, st)          \
+   : mode == tc::kModeBnd ? launch_tc<DP, NS, tc::kModeBnd>(b, status, st)            \
+                          : launch_tc<DP, NS, tc::kModeFp0T>(b, status, st))
+  if (a.d <= 8) return PDEIP_TC_DISPATCH(8, 2);
+  if (a.d <= 16) return PDEIP_TC_DISPATCH(16, 1);
+  return PDEIP_TC_DISPATCH(32, 1);
+#undef PDEIP_TC_DISPATCH
 }
 #endif
 

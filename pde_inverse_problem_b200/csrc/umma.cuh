@@ -56,6 +56,20 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// A operand from TENSOR MEMORY (K-major by construction: lane = row, 32-bit column c = the bf16 pair (k = 2c, 2c + 1)),
+// B from shared memory.  a_tmem addresses the first of the 8 columns of this K = 16 step.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // exactly one lane of a converged warp (the compiler then issues tcgen05.mma / commit without a per-lane
 // "waterfall" loop, which a plain `lane == 0` test provokes)
 __device__ __forceinline__ bool elect_one() {

@@ -10,6 +10,8 @@ namespace pdeip {
 // mode 2: D[m][n] = sum_r A[r][m] * B[r][n]      A [K][128], B [K][N]        (both transposed views)
 // mode 3: TMEM st/ld round trip: D[m][n] = A[m][n] (K = N)
 // mode 4: as mode 2 with the M = 64 instruction shape; TMEM is pre-filled with -777 so the dump shows which lanes are written
+// mode 5: as mode 0 with the A operand read from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): thread = row = TMEM
+//         lane stores its row as packed bf16 pairs, column c = (A[row][2c], A[row][2c+1]), at columns [64, 64 + K/2)
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ B, float* __restrict__ D,
                                                             int K, int N, int* __restrict__ status) {
@@ -17,13 +19,14 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int a_rows = (mode == 2 || mode == 4) ? K : 128, a_cols = (mode == 2 || mode == 4) ? 128 : K;
-  const int b_rows = (mode == 0) ? N : K, b_cols = (mode == 0) ? K : N;
+  const bool a_t = mode == 2 || mode == 4;
+  const int a_rows = a_t ? K : 128, a_cols = a_t ? 128 : K;
+  const int b_rows = (mode == 0 || mode == 5) ? N : K, b_cols = (mode == 0 || mode == 5) ? K : N;
   const uint32_t a_rg = (uint32_t)(a_cols / 8) * 128u, b_rg = (uint32_t)(b_cols / 8) * 128u;
   uint8_t* a_tile = sm;
   uint8_t* b_tile = sm + (size_t)(a_rows / 8) * a_rg;
   if (warp == 0) {
-    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 64);
+    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 128);
     umma::tmem_relinquish();
   }
   if (tid == 0) {
@@ -51,6 +54,22 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   const uint32_t tbase = tmem_base_s;
   const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
   bool ok = true;
+  if (mode == 5) {  // A operand into TMEM: packed bf16 pairs of this thread's row
+    for (int c = 0; c < K / 2; c += 4) {
+      uint32_t w[4];
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 pr = __floats2bfloat162_rn(A[tid * K + 2 * (c + i)], A[tid * K + 2 * (c + i) + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&pr);
+      }
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lane_addr + 64 + c), "r"(w[0]),
+                   "r"(w[1]), "r"(w[2]), "r"(w[3])
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   if (mode == 4) {  // sentinel fill (every warp its own lane quadrant), ordered before the MMA by the barrier below
     float v[8];
     for (int i = 0; i < 8; ++i) v[i] = -777.f;
@@ -71,7 +90,13 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
       if (mode == 0) umma::gemm_kk(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
       else if (mode == 1) umma::gemm_km(tbase, at, a_rg, 0, bt, b_rg, 0, 0, K, N, 0);
       else if (mode == 2) umma::gemm_mm(tbase, at, a_rg, 0, bt, b_rg, 0, K, N, 0);
-      else {
+      else if (mode == 5) {
+        const uint32_t idesc = umma::make_idesc(N, 0, 0);
+        for (int k = 0; k < K; k += 16) {
+          const uint64_t bd = umma::make_desc(bt + (uint32_t)(k >> 3) * 128u, 128u, b_rg);
+          umma::mma_bf16_ts(tbase, tbase + 64 + (uint32_t)(k >> 1), bd, idesc, (k > 0) ? 1u : 0u);
+        }
+      } else {
         const uint32_t idesc = (umma::make_idesc(N, 1, 1) & ~(0x1Fu << 24)) | ((uint32_t)(64 >> 4) << 24);  // M = 64
         for (int k = 0; k < K; k += 16) {
           const uint64_t ad = umma::make_desc(at + (uint32_t)(k >> 3) * a_rg, a_rg, 128u);
@@ -95,7 +120,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const floa
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tbase, 64);
+  if (warp == 0) umma::tmem_dealloc(tbase, 128);
 }
 
 }  // namespace pdeip
@@ -104,7 +129,7 @@ using namespace pdeip;
 
 extern "C" int pdeip_debug_umma(int mode, const float* A, const float* B, float* D, int K, int N, int* status,
                                 void* stream) {
-  PDEIP_REQUIRE(mode >= 0 && mode <= 4 && A && D && status, PDEIP_ERR_INVALID_ARG, "bad arguments");
+  PDEIP_REQUIRE(mode >= 0 && mode <= 5 && A && D && status, PDEIP_ERR_INVALID_ARG, "bad arguments");
   PDEIP_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 64, PDEIP_ERR_INVALID_ARG,
                 "K must be a multiple of 16 in [16,128], N a multiple of 16 in [16,64]");
   const size_t smem = (size_t)128 * 128 * 2 + (size_t)128 * 64 * 2 + 1024;

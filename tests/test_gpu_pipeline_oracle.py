@@ -3,10 +3,10 @@ composition was not): `pipeline.HotPath.step` (chunks, weights 1 / N_global, emi
 BLOCK128 trajectory, boundary sets from z_last / z0, Adam) and an N-iteration `JaxTrainer.fit`, each against the
 float64 oracle fed with the SAME Philox draws / the SAME batches.
 
-Tolerances.  Linear (contractive) drift, fp32 path: the north-star's 1e-5 class is asserted on the whole composition.
-GMM drift, S = 200: float32 trajectories are not reproducible to 1e-5 by ANY implementation (the
-same code in float32 vs float64 differs by 3e-5 after 200 steps, locally unstable trajectories between modes), so the
-fp32 composition is asserted at 2e-4 on loss / gradient; the tensor path at the bf16-GEMM tolerance 1e-2."""
+Tolerances.  fp32 path: the north-star's 1e-5 class is asserted on the whole composition (loss, "loss ground truth",
+gradient, gradient norm), for the linear drift AND for the GMM drift at S = 200: individual float32 trajectories
+deviate from float64 by up to 3e-5 after 200 steps, but the loss and the gradient are ensemble means
+and come out at 1e-7 .. 1e-6 (measured, printed by the tests).  Tensor path: the bf16-GEMM tolerance 1e-2."""
 import pytest
 import torch
 
@@ -107,17 +107,21 @@ def test_hotpath_step_c3_shape_vs_oracle(cuda, path_name):
     """C3 shape (KGMM d = 8, K = 16, S = 200), 2 chunks of 128 particles (BLOCK128 trajectory), both paths, against the
     float64 closed-form twin on the same Philox draws."""
     e = _hotpath_vs_oracle(cuda, d=8, K=16, n=256, S=200, chunk=128, path_name=path_name, use_autodiff=False)
-    tol = 2e-4 if path_name == "fp32" else 1e-2
+    tol = 1e-5 if path_name == "fp32" else 1e-2
     assert e["loss"] < tol and e["gt"] < tol and e["grad"] < tol and e["gnorm"] < tol, e
-    assert e["params"] < (1e-4 if path_name == "fp32" else 5e-3), e  # one Adam step of size lr = 1e-2
+    # One Adam step: the first update is lr * g / (|g| + eps) per entry, i.e. it AMPLIFIES the relative error of the small
+    # gradient entries (max-norm-small errors flip u between -1 and 1), so the updated parameters are compared on the
+    # fp32 path only; the tensor path's gradient itself is checked above.
+    if path_name == "fp32":
+        assert e["params"] < 1e-5, e
 
 
 @pytest.mark.parametrize("path_name", ["fp32", "tensor"])
 def test_hotpath_step_vs_autodiff_oracle(cuda, path_name):
-    """The same composition against the AUTODIFF restatement (oracle/residuals.py), S = 40, ragged last chunk (n = 320,
-    chunk = 192: a BLOCK128 chunk of 128 + ... and a 128-particle tail), GMM drift."""
+    """The same composition against the AUTODIFF restatement (oracle/residuals.py), S = 40, n = 320 with chunk = 192: a
+    192-particle chunk (not a multiple of 128: time-SoA trajectory layout) and a 128-particle tail (BLOCK128), GMM drift."""
     e = _hotpath_vs_oracle(cuda, d=8, K=16, n=320, S=40, chunk=192, path_name=path_name, use_autodiff=True)
-    tol = 5e-5 if path_name == "fp32" else 1e-2
+    tol = 1e-5 if path_name == "fp32" else 1e-2
     assert e["loss"] < tol and e["gt"] < tol and e["grad"] < tol, e
 
 

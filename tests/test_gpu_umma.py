@@ -55,3 +55,15 @@ def test_m64_instruction_shape_lane_mapping(cuda):
         assert torch.allclose(D[lane], ref[i], rtol=1e-4, atol=1e-4), i
     untouched = [l for l in range(128) if (l % 32) >= 16]
     assert torch.all(D[untouched] == -777.0)
+
+
+@pytest.mark.parametrize("K,N", [(16, 32), (32, 32), (64, 32), (48, 48)])
+def test_a_operand_from_tensor_memory(cuda, K, N):
+    """tcgen05.mma with the A operand in TMEM (thread = row = lane stores its row as packed bf16 pairs, 32-bit column c =
+    elements k = 2c, 2c + 1; 8 columns per K = 16 step), B K-major in shared memory: D = A B^T."""
+    g = torch.Generator().manual_seed(K * 7 + N)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    A = bf(torch.randn(128, K, generator=g)).to(cuda)
+    B0 = bf(torch.randn(N, K, generator=g)).to(cuda)
+    D = _run(5, A, B0, K, N, cuda)
+    assert torch.allclose(D, A @ B0.T, rtol=1e-4, atol=1e-4)
