@@ -16,7 +16,7 @@ Default workload: C5 (BASELINE.json configs[4], the north-star's scaling target)
 rank) is measured in the same run and reported as `extra.c3`.  C2 / C3 / C4 as --workload keep a fixed ensemble per
 rank ("weak").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5] [--path fp32|tensor]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C4mf|C5] [--path fp32|tensor]
     python bench.py --impl reference ...     # CPU restatement of the reference (oracle port) on host cores
 """
 from __future__ import annotations
@@ -44,6 +44,9 @@ WORKLOADS = {
                gamma=0.5, chunk=303104),  # two whole waves of the tcgen05 integrator grid (148 SMs x 8 CTAs x 128 particles)
     "C4": dict(name="KMV-quadratic (-A x drift) d=16 N=2^22 S=100", d=16, K=0, n=1 << 22, S=100, T=2.0,
                gamma=1.0, chunk=1 << 18),
+    "C4mf": dict(name="KMV interacting system d=16 N=2^22 S=100: drift A (x - xbar_t), xbar_t the empirical mean of ALL "
+                      "ranks' particles (README.md:54-62); one noise pre-pass + ONE all-reduce per iteration",
+                 d=16, K=0, n=1 << 22, S=100, T=2.0, gamma=1.0, chunk=1 << 18, meanfield=True),
     "C5": dict(name="KGMM d=32 K=64 N=2^24 total S=200, sharded over the ranks", d=32, K=64, n_total=1 << 24, S=200,
                T=2.0, gamma=0.5, chunk=56832),  # 148 SMs x 3 CTAs x 128 particles: one full wave of the tcgen05 integrator
 }
@@ -146,7 +149,7 @@ def build_problem(w, device, seed=1):
     else:       # OU.py:15-43: tilde_F = _F _F^T (scaled by 1/d so that dt*lambda_max stays stable at every d)
         _F = torch.randn(d, d + 1, generator=g, dtype=torch.float64)
         drift = ((_F @ _F.T) / d).float().to(device)
-        drift_kind = L.DRIFT_LINEAR
+        drift_kind = L.DRIFT_MEANFIELD_TABLE if w.get("meanfield") else L.DRIFT_LINEAR
         true = ops.TrueGrad(L.DRIFT_LINEAR, drift)
         cov_half = None
     model = V_hypothesis(1, [HIDDEN] * LAYERS, d)
@@ -352,7 +355,7 @@ def oracle_step(w, n_s, seed=0):
     else:
         pde = o_prob.KineticOUProblem(d, T=w["T"], dtype=torch.float32)
         pde.initial_configuration["tilde_F"] = pde.initial_configuration["tilde_F"] / d
-        grad_fn = o_pot.LinearDrift(pde.initial_configuration["tilde_F"]).gradient
+        grad_fn = o_pot.LinearDrift(pde.initial_configuration["tilde_F"], mean_field=bool(w.get("meanfield"))).gradient
     pde.initial_configuration["gamma_friction"] = w["gamma"]
     params = o_model.init_mlp_params(d, HIDDEN, LAYERS, dtype=torch.float32)
     z0 = torch.randn(n_s, 2 * d, generator=g)

@@ -66,6 +66,17 @@ constexpr uint32_t C_ZG0 = C_R + 64, C_ZG1 = C_R + 96, C_UG = C_R + 48;     // P
 constexpr uint32_t C_AB2 = C_R + 16, C_AA2R = C_R + 96;                     // P9
 constexpr uint32_t C_AB1 = C_R + 48, C_AA1R = C_R + 96;                     // P10
 
+// PDEIP_TC_TS (off by default; round-1 verdict item 1a, built and measured in round 2).  One-slot kernels (d > 8) use 312
+// of the 512 TMEM columns: the next 48 can hold the A OPERAND of the layer GEMMs (tcgen05.mma [d], [a_tmem], b_desc:
+// lane = point row, column c = the bf16 pair (k = 2c, 2c + 1) of that row): the epilogue thread that packs an 8-unit
+// chunk for the shared-memory tile (which the batch-reduced dW GEMMs still read through the transposed view) also stores
+// the same four words to TMEM.  Correct (tests/test_gpu_umma.py::test_a_operand_from_tensor_memory, all tensor-path
+// tests), but it does NOT shorten the GEMM phases: the phase trace shows the same 60-75 cycles per 128 x 32..48 x 16 MMA
+// with the A operand in TMEM as in shared memory (P1: 8 MMAs in 527 cycles either way), i.e. the instruction is paced by
+// its accumulator traffic (a 16 KB fp32 tile read and written per K = 16 step), not by the A fetch, and the extra
+// tcgen05.st + wait::st and 400 B more spills cost 11 % at d = 32 (1.94e9 -> 1.72e9 evals/s).
+constexpr uint32_t C_AOP = C_SLOT0 + SLOT_COLS;  // [312, 360): columns = 4 x (chunk index within the operand)
+
 // ---- shared memory ---------------------------------------------------------------------------------------------
 // Z tile chunk map (24 chunks of 8 columns)
 constexpr int ZC_ZA2 = 0, ZC_ZA1 = 6, ZC_ZA0 = 10, ZC_TA = 14, ZC_TB = 20;
@@ -200,6 +211,50 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, Desc a, uint32_t a_adv, Des
       : "memory");
 }
 
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, Desc b, uint32_t b_adv, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b.lo + (b_adv >> 4)), "r"(b.hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same GEMMs with the A operands in TMEM: a_col[g] = first TMEM column of stream g's operand (8 columns per k-step)
+template <int K, int N, int NG, bool LO = true, int NLO = NG>
+__device__ __forceinline__ void mm_fwd_ts(const uint32_t (&d)[NG], const uint32_t (&a_col)[NG], Desc w_hi, Desc w_lo) {
+  constexpr uint32_t idesc = make_idesc(N, 0, 0);
+#pragma unroll
+  for (int k = 0; k < K; k += 16)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) mma_ts(d[g], a_col[g] + (k >> 1), w_hi, k * 16, idesc, k > 0 ? 1u : 0u);
+  if constexpr (LO) {
+#pragma unroll
+    for (int k = 0; k < K; k += 16)
+#pragma unroll
+      for (int g = 0; g < NLO; ++g) mma_ts(d[g], a_col[g] + (k >> 1), w_lo, k * 16, idesc, 1u);
+  }
+}
+template <int K, int N, int NG, bool LO = true, int NLO = NG>
+__device__ __forceinline__ void mm_bwd_ts(const uint32_t (&d)[NG], const uint32_t (&a_col)[NG], Desc w_hi_m, Desc w_lo_m,
+                                          uint32_t w_rg) {
+  constexpr uint32_t idesc = make_idesc(N, 0, 1);
+#pragma unroll
+  for (int k = 0; k < K; k += 16)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) mma_ts(d[g], a_col[g] + (k >> 1), w_hi_m, (k >> 3) * w_rg, idesc, k > 0 ? 1u : 0u);
+  if constexpr (LO) {
+#pragma unroll
+    for (int k = 0; k < K; k += 16)
+#pragma unroll
+      for (int g = 0; g < NLO; ++g) mma_ts(d[g], a_col[g] + (k >> 1), w_lo_m, (k >> 3) * w_rg, idesc, 1u);
+  }
+}
+
 // NG independent forward GEMMs D_g[128 x N] = A_g(K-major, K columns) * W^T(K-major tile [N][K]), hi + lo halves of
 // the weights, issued round-robin over g.  a_off[g] / d[g]: byte offset of the A band / TMEM column of GEMM g.
 // NLO: the lo weight halves are applied to the first NLO of the NG streams only
@@ -271,6 +326,15 @@ __device__ __forceinline__ void put_chunk(uint8_t* tile, uint32_t off, const flo
   uint4 q;
   q.x = pack2(v[0], v[1]); q.y = pack2(v[2], v[3]); q.z = pack2(v[4], v[5]); q.w = pack2(v[6], v[7]);
   *reinterpret_cast<uint4*>(tile + off) = q;
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t* r);
+// the chunk to shared memory AND (TS) the same four packed words to the A-operand columns of this thread's TMEM lane
+template <bool TS>
+__device__ __forceinline__ void put_op(uint8_t* tile, uint32_t off, uint32_t taddr, const float* v) {
+  uint4 q;
+  q.x = pack2(v[0], v[1]); q.y = pack2(v[2], v[3]); q.z = pack2(v[4], v[5]); q.w = pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + off) = q;
+  if constexpr (TS) tm_st4(taddr, reinterpret_cast<const uint32_t*>(&q));
 }
 // TMEM: raw loads (no wait), 8 or 16 consecutive 32-bit columns of this thread's lane
 __device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t* r) {
@@ -411,6 +475,10 @@ constexpr int kModeKfp0T = 0, kModeBnd = 1, kModeFp0T = 2;
 template <int DP, int NS, int MODE>
 __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
   constexpr bool BND = MODE == kModeBnd, FPM = MODE == kModeFp0T;
+#ifndef PDEIP_TC_TS
+#define PDEIP_TC_TS 0  // measured (profiles/r02_summary_residual.md): no gain, see C_AOP above
+#endif
+  constexpr bool kTS = PDEIP_TC_TS && NS == 1;  // layer-GEMM A operands from TMEM (the two-slot kernel has no columns left)
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -530,6 +598,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
           const uint32_t TS = TB + C_SLOT0 + (uint32_t)s * SLOT_COLS;
           const uint32_t mb = smem_u32(mbar_p + s);
+          const uint32_t AOP = TB + C_AOP;  // A-operand columns (kTS)
           const Desc XK = mk_desc(sb + S::O_X, 128, S::RG_X), A1K = mk_desc(sb + S::O_A1, 128, S::RG_A),
                      A2K = mk_desc(sb + S::O_A2, 128, S::RG_A), ZK = mk_desc(sb + S::O_Z, 128, S::RG_Z);
           const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
@@ -539,32 +608,43 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
             TC_TRACE(4);
             switch (ph) {
               case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
-                mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
-                mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
+                if constexpr (kTS) {
+                  mm_fwd_ts<S::KX, 32, 1>({TS + C_Z0}, {AOP}, T0XHK, T0XLK);
+                  mm_fwd_ts<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, {AOP + S::KX / 2}, T0VHK, T0VLK);
+                } else {
+                  mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
+                  mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
+                }
                 commit(mb);
               } break;
               case 1: {  // z1, z1_1, z2^_1
-                mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
+                if constexpr (kTS) mm_fwd_ts<32, 32, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, {AOP + 4 * AC_T, AOP + 4 * AC_A1, AOP + 4 * AC_C}, T1HK, T1LK);
+                else mm_fwd<32, 32, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_Z1, TS + C_Z11, TS + C_Z21}, A1K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T1HK, T1LK);
                 commit(mb);
               } break;
               case 2: {  // u, u1, u2^
-                mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
+                if constexpr (kTS) mm_fwd_ts<32, OP, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_U, TS + C_U1, TS + C_U2}, {AOP + 4 * AC_T, AOP + 4 * AC_A1, AOP + 4 * AC_C}, T2HK, T2LK);
+                else mm_fwd<32, OP, 3, PDEIP_TC_LO_FWD, kNloFwd>({TS + C_U, TS + C_U1, TS + C_U2}, A2K, {AC_T * CH, AC_A1 * CH, AC_C * CH}, T2HK, T2LK);
                 commit(mb);
               } break;
               case 3: {  // aa2 = za2 W2^T, ab1_2 = s1v W2^T;  dW2 += a1_2^T s1v
-                mm_bwd<OP, 32, 2, true, kNloBwd>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
+                if constexpr (kTS) mm_bwd_ts<OP, 32, 2, true, kNloBwd>({TS + C_AA2, TS + C_AB12}, {AOP, AOP + 24}, T2HM, T2LM, S::RG_T2);
+                else mm_bwd<OP, 32, 2, true, kNloBwd>({TS + C_AA2, TS + C_AB12}, ZK, {ZC_ZA2 * CH, ZC_TA * CH}, T2HM, T2LM, S::RG_T2);
                 commit(mb);
               } break;
               case 4: {  // aa1 = za1 W1^T, ab1_1 = zbar1' W1^T;  dW1 += a1_1^T zbar1'
-                mm_bwd<32, 32, 2, true, kNloBwd>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
+                if constexpr (kTS) mm_bwd_ts<32, 32, 2, true, kNloBwd>({TS + C_AA1, TS + C_AB11}, {AOP, AOP + 16}, T1HM, T1LM, S::RG_T1);
+                else mm_bwd<32, 32, 2, true, kNloBwd>({TS + C_AA1, TS + C_AB11}, ZK, {ZC_ZA1 * CH, ZC_TB * CH}, T1HM, T1LM, S::RG_T1);
                 commit(mb);
               } break;
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
-                mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
+                if constexpr (kTS) mm_bwd_ts<32, S::KV, 1>({TS + C_G}, {AOP}, T0VHM, T0VLM, S::RG_T0V);
+                else mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
                 commit(mb);
               } break;
               case 6: {  // zg^_0 = g^ W0
-                mm_fwd<S::KV, 32, 1, false>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
+                if constexpr (kTS) mm_fwd_ts<S::KV, 32, 1, false>({TS + C_ZG0}, {AOP}, T0VHK, T0VLK);
+                else mm_fwd<S::KV, 32, 1, false>({TS + C_ZG0}, XK, {S::XC_G * CH}, T0VHK, T0VLK);
                 commit(mb);
 #if PDEIP_TC_G_CHAIN_EARLY
                 // dW0 += g^^T za0: both operands are final since E6 / E5, and the tensor pipe idles through P6..P8 (1-2
@@ -573,7 +653,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
               } break;
               case 7: {  // zg^_1 = ag^_1 W1  (operand in the a1 band)
-                mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
+                if constexpr (kTS) mm_fwd_ts<32, 32, 1, false>({TS + C_ZG1}, {AOP}, T1HK, T1LK);
+                else mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
                 if constexpr (kCChainsEarly) {  // dW1 += c_1^T za1: c_1 is final since E7 (just arrived), za1 since E4
                   const Desc A1M = mk_desc(sb + S::O_A1, S::RG_A, 128);
@@ -581,7 +662,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 }
               } break;
               case 8: {  // ug^ = ag^_2 W2
-                mm_fwd<32, OP, 1, false>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
+                if constexpr (kTS) mm_fwd_ts<32, OP, 1, false>({TS + C_UG}, {AOP}, T2HK, T2LK);
+                else mm_fwd<32, OP, 1, false>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
                 commit(mb);
                 if constexpr (kCChainsEarly) {  // dW2 += c_2^T za2: c_2 is final since E8 (just arrived), za2 since E3
                   const Desc A2M = mk_desc(sb + S::O_A2, S::RG_A, 128);
@@ -589,11 +671,21 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 }
               } break;
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
-                mm_bwd<OP, 32, 2, BND, 1>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                if constexpr (kTS) {  // s0 from TMEM; za2 (written in E3) only exists in shared memory by now
+                  mm_bwd_ts<OP, 32, 1, BND, 1>({TS + C_AB2}, {AOP}, T2HM, T2LM, S::RG_T2);
+                  mm_bwd<OP, 32, 1, false>({TS + C_AA2R}, ZK, {ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                } else {
+                  mm_bwd<OP, 32, 2, BND, 1>({TS + C_AB2, TS + C_AA2R}, ZK, {ZC_TA * CH, ZC_ZA2 * CH}, T2HM, T2LM, S::RG_T2);
+                }
                 commit(mb);
               } break;
               case 10: {  // ab_1 = zbar0' W1^T, aa1 again;  dW1 += t1^T zbar0' + c_1^T za1
-                mm_bwd<32, 32, 2, BND, 1>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                if constexpr (kTS) {
+                  mm_bwd_ts<32, 32, 1, BND, 1>({TS + C_AB1}, {AOP}, T1HM, T1LM, S::RG_T1);
+                  mm_bwd<32, 32, 1, false>({TS + C_AA1R}, ZK, {ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                } else {
+                  mm_bwd<32, 32, 2, BND, 1>({TS + C_AB1, TS + C_AA1R}, ZK, {ZC_TB * CH, ZC_ZA1 * CH}, T1HM, T1LM, S::RG_T1);
+                }
                 commit(mb);
               } break;
               default: {  // dW0 += x_hi^T zbar0'' (+ x_lo^T zbar0'' if PDEIP_TC_XLO_DW) + g^^T za0
@@ -674,6 +766,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     const uint32_t offA = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_A;
     const uint32_t offZ = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * S::RG_Z;
     const uint32_t LA0 = TB + ((uint32_t)(q * 32) << 16) + C_SLOT0;
+    const uint32_t LOP = TB + ((uint32_t)(q * 32) << 16) + C_AOP;  // this thread's lane of the A-operand columns (kTS)
     const int u16 = 16 * half, u24 = 24 * half;  // first unit owned in 32- / 48-unit tiles
     // prefetched input chunks: item j = half + 2 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
     constexpr int NI = (3 * S::XC + 1) / 2;
@@ -792,13 +885,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
                 lo[e] = xv - hi[e];
               }
-              put_chunk(X, (S::XC_HI + cg) * 128, hi);
-              put_chunk(X, (S::XC_LO + cg) * 128, lo);
+              put_op<kTS>(X, (S::XC_HI + cg) * 128, LOP + 4 * cg, hi);
+              put_op<kTS>(X, (S::XC_LO + cg) * 128, LOP + 4 * (S::XC + cg), lo);
             } else if (band == 1) {
               float vv[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) vv[e] = (valid && cg * 8 + e < d) ? xin[i][e] : 0.f;
-              put_chunk(X, (S::XC_V + cg) * 128, vv);
+              put_op<kTS>(X, (S::XC_V + cg) * 128, LOP + S::KX / 2 + 4 * cg, vv);
             }
           }
         };
@@ -842,9 +935,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          put_chunk(At, (AC_T + 2 * half + c) * 128, t + 8 * c);
-          put_chunk(At, (AC_A1 + 2 * half + c) * 128, q1 + 8 * c);
-          put_chunk(At, (AC_C + 2 * half + c) * 128, q2 + 8 * c);
+          put_op<kTS>(At, (AC_T + 2 * half + c) * 128, LOP + 4 * (AC_T + 2 * half + c), t + 8 * c);
+          put_op<kTS>(At, (AC_A1 + 2 * half + c) * 128, LOP + 4 * (AC_A1 + 2 * half + c), q1 + 8 * c);
+          put_op<kTS>(At, (AC_C + 2 * half + c) * 128, LOP + 4 * (AC_C + 2 * half + c), q2 + 8 * c);
         }
         tm_park<16>(LA + (l1 ? C_S1P1 : C_S1P2) + 8 * half, s1);
         TC_PROBE(l1 ? 0 : 3, u16, t, 16);
@@ -896,8 +989,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          put_chunk(Z, (ZC_ZA2 + 3 * half + c) * 128, za + 8 * c);
-          put_chunk(Z, (ZC_TA + 3 * half + c) * 128, sv + 8 * c);
+          put_op<kTS>(Z, (ZC_ZA2 + 3 * half + c) * 128, LOP + 4 * (3 * half + c), za + 8 * c);
+          put_op<kTS>(Z, (ZC_TA + 3 * half + c) * 128, LOP + 24 + 4 * (3 * half + c), sv + 8 * c);
         }
         tm_park<24>(LA + C_S0P + 12 * half, sp);
         // this thread's share of D_v V = 2 u.u1 and D_v^2 V = 2 (u1.u1 + u.u2), u2 = -2 u2^
@@ -948,8 +1041,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          put_chunk(Z, ((l2 ? ZC_ZA1 : ZC_ZA0) + 2 * half + c) * 128, za + 8 * c);
-          put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
+          put_op<kTS>(Z, ((l2 ? ZC_ZA1 : ZC_ZA0) + 2 * half + c) * 128, LOP + 4 * (2 * half + c), za + 8 * c);
+          // zbar1' is an A operand of P4; zbar1'' (E5) only feeds the dW0 chain (shared memory)
+          put_op<(kTS && l2)>(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, LOP + 16 + 4 * (2 * half + c), zb + 8 * c);
         }
         TC_FINE(1);
         tm_park<16>(LA + (l2 ? C_PZ2 : C_PZ1) + 8 * half, pz);
@@ -977,7 +1071,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
               float gh[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) gh[e] = (0.125f * cgw) * g4[e];  // the g-stream is linear in its direction: c_g g / 2
-              put_chunk(X, (S::XC_G + cg) * 128, gh);
+              put_op<kTS>(X, (S::XC_G + cg) * 128, LOP + 4 * cg, gh);
               TC_PROBE(15, cg * 8, gv, 8);
             }
             if (own_sum) {
@@ -1028,7 +1122,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          put_chunk(At, (AC_A1 + 2 * half + c) * 128, ag + 8 * c);
+          put_op<kTS>(At, (AC_A1 + 2 * half + c) * 128, LOP + 4 * (2 * half + c), ag + 8 * c);
           put_chunk(At, (AC_C + 2 * half + c) * 128, cc + 8 * c);
         }
         TC_PROBE(l1 ? 16 : 17, u16, cc, 16);
@@ -1056,7 +1150,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
 #endif
 #pragma unroll
-        for (int c = 0; c < 3; ++c) put_chunk(Z, (ZC_TA + 3 * half + c) * 128, s0 + 8 * c);
+        for (int c = 0; c < 3; ++c) put_op<kTS>(Z, (ZC_TA + 3 * half + c) * 128, LOP + 4 * (3 * half + c), s0 + 8 * c);
         TC_PROBE(18, u24, s0, 24);
       } else {
         // E10: zbar0' = s1_2 ab_2 + pz2 - 2 t2 aa^2 c_2;  db1       E11: zbar0'' likewise with hidden layer 1;  db0
@@ -1105,9 +1199,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
 #endif
 #pragma unroll
-        for (int c = 0; c < 2; ++c) put_chunk(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, zb + 8 * c);
+        for (int c = 0; c < 2; ++c)  // zbar0' is an A operand of P10; zbar0'' (E11) only feeds the dW0 chain
+          put_op<(kTS && l2)>(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, LOP + 4 * (2 * half + c), zb + 8 * c);
         TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
       }
+      if constexpr (kTS) tm_wait_st();  // the A-operand columns are complete before the hand-off
       TC_TRACE(7);
 #ifdef PDEIP_TC_TRACE
       fence_async_smem();

@@ -14,12 +14,13 @@ d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n = (1 << 18) * 200
 model = V_hypothesis(1, [32, 32], d)
 flat = model.flat(model.init(11, torch.zeros(d, device=cuda)))
-pts = torch.randn(3 * d, n, device=cuda)
+layout = {"soa": L.LAYOUT_SOA, "blk": L.LAYOUT_BLOCK128}[sys.argv[2] if len(sys.argv) > 2 else "blk"]  # blk = the pipeline's layout
+pts = torch.randn(3 * d, n, device=cuda) if layout == L.LAYOUT_SOA else torch.randn(n // 128, 3 * d, 128, device=cuda)
 spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
 acc = ops.ResidualAccumulator(spec, device=cuda).begin()
 tg = ops.TrueGrad(L.DRIFT_IN_POINTS)
 for _ in range(2):
-    acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=tg)
+    acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=layout, path=L.PATH_TENSOR, true_grad=tg)
 torch.cuda.synchronize()
 lib = C.CDLL(L.LIB_PATH)
 lib.pdeip_debug_tensor_trace.argtypes = [C.c_void_p, C.c_int]
@@ -47,7 +48,7 @@ print("first mbarrier poll per (ph, slot): latency cycles / hit:",
 e0 = torch.cuda.Event(enable_timing=True)
 e1 = torch.cuda.Event(enable_timing=True)
 e0.record()
-acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=L.LAYOUT_SOA, path=L.PATH_TENSOR, true_grad=tg)
+acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=layout, path=L.PATH_TENSOR, true_grad=tg)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
