@@ -422,3 +422,68 @@ def test_timed_out_tensor_phase_poisons_loss_and_gradient(cuda):
     acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, path=L.PATH_TENSOR)
     sums, grad = acc.finalize()
     assert torch.isfinite(sums[L.SUM_LOSS]) and torch.isfinite(grad).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases of the round-2 paths
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 127, 129, 300])
+def test_fp_and_boundary_tensor_modes_edge_sizes(cuda, n):
+    """Empty, single-point and tile-boundary point counts through the FP 0T direction tiles and the KFP boundary mode of the
+    tcgen05 kernel: agreement with the fp32 kernel (n = 0 is a no-op)."""
+    ops, L = _ops()
+    d = 4
+    spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
+    g = torch.Generator().manual_seed(n + 5)
+    flat = o_model.flatten_params(o_model.init_mlp_params(d, 32, 2, seed=3)).float().to(cuda)
+    x = (torch.randn(n, d, generator=g) * 1.5).to(cuda)
+    z = (torch.randn(n, 2 * d, generator=g) * 1.2).to(cuda)
+    res = {}
+    for name, path in (("fp32", L.PATH_FP32), ("tensor", L.PATH_TENSOR)):
+        acc = ops.ResidualAccumulator(spec, device=cuda).begin()
+        acc.accumulate(L.SET_FP_0T, flat, x, 1.0 / max(n, 1), path=path)
+        s1, g1 = (t.cpu().double().clone() for t in acc.finalize())
+        acc.begin()
+        acc.accumulate(L.SET_KFP_BOUNDARY, flat, z, 1.0 / max(n, 1), coef=-1.0, path=path)
+        s2, g2 = (t.cpu().double().clone() for t in acc.finalize())
+        res[name] = (s1, g1, s2, g2)
+    assert ops.tensor_path_status() == 0
+    if n == 0:
+        for t in res["tensor"]:
+            assert float(t.abs().sum()) == 0.0
+        return
+    tol = 1e-2 if n >= 128 else 3e-2  # fewer points than a tile: single-point bf16 rounding, nothing averages
+    s1, g1, s2, g2 = res["fp32"]
+    t1, h1, t2, h2 = res["tensor"]
+    assert relmax(t1[L.SUM_LOSS], s1[L.SUM_LOSS]) < tol and relmax(h1, g1) < tol
+    assert relmax(h2, g2) < tol
+
+
+@pytest.mark.parametrize("d,n,S", [(3, 77, 7), (5, 130, 1), (2, 1, 4)])
+def test_meanfield_table_generic_kernel_ragged(cuda, d, n, S):
+    """Mean-field table on the generic integrator: d not a multiple of 4, n not a multiple of 128, a single particle
+    (the ensemble mean is the particle itself: the drift vanishes) and a single step."""
+    ops, L = _ops()
+    T, gamma, seed = 0.5, 0.7, 8
+    dt = T / S
+    A = _spd(d, 31 + d)
+    g = torch.Generator().manual_seed(d * 100 + n)
+    z0 = (torch.randn(n, 2 * d, generator=g, dtype=torch.float64) - 0.3).float()
+    sums = ops.meanfield_noise_sums(z0.to(cuda), S, seed)
+    params, xbar = ops.meanfield_drift_params(sums, n, A.float().to(cuda), S, dt, gamma)
+    noise = ops.philox_normals(n, S + 1, d, seed=seed, device=cuda).double().cpu()
+    last, traj, xbars, _ = _oracle_interacting(z0.double(), S, dt, gamma, A, noise)
+    zl, tr, _ = ops.kl_integrate(z0.to(cuda), S, dt, gamma, L.DRIFT_MEANFIELD_TABLE, params, seed=seed)
+    assert relmax(xbar, xbars) < 1e-5 and relmax(tr, traj) < 1e-5 and relmax(zl, last) < 1e-5
+
+
+def test_kmv_reference_set_of_one_and_full_agree_with_oracle(cuda):
+    """m = 1 (a single reference trajectory) and m = n through the same entry points."""
+    _, L = _ops()
+    n, d, nt = 23, 2, 2
+    pde, apply_fn, params, data0T, tau, run = _kmv_case(cuda, "mlp", d, nt, n, seed=77)
+    for m in (1, n):
+        ref = o_res.kmv_value_and_grad_fn(apply_fn, params, {"0T": data0T, "tau_0T": tau}, pde, m=m)
+        sums, gflat = run(m=m)
+        assert relmax(sums[L.SUM_LOSS], ref["loss"]) < 1e-5
+        assert relmax(gflat, o_model.flatten_params(ref["grad"])) < 1e-5
