@@ -20,6 +20,8 @@ from .optimizer import AdamL2
 class JaxTrainer:
     """Name kept for drop-in compatibility with the reference's `from core.trainer import JaxTrainer`."""
 
+    EMA_START_EPOCH = 40000  # core/trainer.py:87,97 (hard-coded in the reference; an attribute here so tests can reach it)
+
     def __init__(self, cfg, method, rng, optimizer: AdamL2, forward_fn, params,
                  log_fn: Optional[Callable[[Dict, int], None]] = None, nan_check_every: int = 1):
         self.cfg = cfg
@@ -59,8 +61,8 @@ class JaxTrainer:
             rng_train, rng_test, rng_plot = jrandom.split(rngs[epoch], 3)
             v_g_etc = self.value_and_grad_fn_efficient(self.params, rng_train)
             use_ema = False
-            if cfg.train.optimizer.use_ema and epoch >= 40000:      # trainer.py:87-103
-                if epoch == 40000:
+            if cfg.train.optimizer.use_ema and epoch >= self.EMA_START_EPOCH:      # trainer.py:87-103
+                if epoch == self.EMA_START_EPOCH:
                     ema.copy_(self.params["_flat"])                  # EmaState(count=0, ema=params)
                 use_ema = True
             self.optimizer.step(self.params, v_g_etc["grad"], opt_state, ema=ema, use_ema=use_ema, norms=norms)

@@ -132,10 +132,14 @@ def test_hotpath_step_linear_drift_fp32_1e5(cuda):
     assert e["loss"] < 1e-5 and e["gt"] < 1e-5 and e["grad"] < 1e-5, e
 
 
-def test_trainer_fit_20_iterations_vs_oracle_loop(cuda):
+@pytest.mark.parametrize("ema_start", [None, 6])
+def test_trainer_fit_20_iterations_vs_oracle_loop(cuda, ema_start):
     """core/trainer.py:61-107 on the CUDA path against an oracle loop (oracle/residuals.py + oracle/optim.py) on
     IDENTICAL batches: the batches the method samples on the device are captured and fed to the float64 oracle,
-    parameters are compared after every one of 20 iterations (cosine schedule, L2-in-Adam)."""
+    parameters are compared after every one of 20 iterations (cosine schedule, L2-in-Adam).  ema_start = 6: the EMA
+    branch of the trainer (trainer.py:87-103: state re-seeded with the parameters at the switch epoch — 40 000 in the
+    reference, moved to 6 here —, then every step ema <- 0.999 ema + 0.001 p_new and the parameters are OVERWRITTEN by
+    the raw accumulator)."""
     from pde_inverse_problem_b200 import registry
     from pde_inverse_problem_b200.config import make_config
     from pde_inverse_problem_b200.core.optimizer import get_optimizer
@@ -146,7 +150,8 @@ def test_trainer_fit_20_iterations_vs_oracle_loop(cuda):
         "neural_network.hidden_dim": 32, "neural_network.layers": 2, "train.number_of_iterations": n_iter,
         "train.optimizer.learning_rate.initial": 1e-2, "train.optimizer.learning_rate.scheduling": "cosine",
         "test.frequency": 1000, "estimation_mode": "non-parametric", "pde_instance.domain_dim": d,
-        "solver.train.batch_size_0T": 600, "solver.train.batch_size_init": 400, "solver.train.batch_size_terminal": 400})
+        "solver.train.batch_size_0T": 600, "solver.train.batch_size_init": 400, "solver.train.batch_size_terminal": 400,
+        "train.optimizer.use_ema": ema_start is not None})
     pde = registry.get_pde_instance(cfg)(cfg=cfg, rng=1, device=cuda)
     method = registry.get_method(cfg)(pde_instance=pde, cfg=cfg, rng=2)
     net, params = method.create_model_fn()
@@ -169,6 +174,8 @@ def test_trainer_fit_20_iterations_vs_oracle_loop(cuda):
 
     trainer = JaxTrainer(cfg=cfg, method=method, rng=R.PRNGKey(3), optimizer=get_optimizer(cfg.train.optimizer),
                          forward_fn=net.apply, params=params, log_fn=log_fn)
+    if ema_start is not None:
+        trainer.EMA_START_EPOCH = ema_start
     trainer.fit()
     assert len(batches) == n_iter and len(snaps) == n_iter
 
@@ -184,7 +191,12 @@ def test_trainer_fit_20_iterations_vs_oracle_loop(cuda):
     for it in range(n_iter):
         ref = o_res.kfp_value_and_grad_fn(o_model.mlp_apply, _oracle_params_from(flat, d), batches[it], opde)
         gflat = o_model.flatten_params(ref["grad"])
+        if ema_start is not None and it == ema_start:
+            ema = flat.clone()                                   # EmaState(count=0, ema=params), trainer.py:97-100
         flat = o_optim.adam_l2_step(flat, gflat, st, sched)
+        if ema_start is not None and it >= ema_start:
+            ema = o_optim.ema_update(ema, flat)                  # trainer.py:67-69: params <- raw ema accumulator
+            flat = ema.clone()
         worst["params"] = max(worst["params"], relmax(snaps[it], flat))
         worst["loss"] = max(worst["loss"], relmax(logs[it]["loss"], ref["loss"]))
         worst["gnorm"] = max(worst["gnorm"], relmax(logs[it]["grad_norm"], ref["grad_norm"]))
