@@ -101,7 +101,20 @@ struct Cfg {
                             O_T0VL = O_T0VH + SZ_T0V, O_T1H = O_T0VL + SZ_T0V, O_T1L = O_T1H + SZ_T1,
                             O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2, O_BIAS = O_T2L + SZ_T2;
   static constexpr uint32_t TP_BYTES = NS == 2 ? 2048 : 4096;
-  static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, TOTAL = O_MISC + 128;
+  // PDEIP_TC_STAGE (off by default; round-1 verdict item 8, built and measured in round 2).  One-slot kernels have shared
+  // memory to spare: the next tile of a BLOCK128 point set ([3 DP][128] floats, one contiguous block) can be staged by ONE
+  // bulk copy of the TMA unit (cp.async.bulk global -> shared, mbarrier complete_tx; UBLKCP in SASS) issued five phases
+  // ahead, instead of 48 LDG per thread behind a bulk L2 prefetch, and E0 / E6 read their row from it.  Correct (all GPU
+  // tests pass with it), but 5-7 % SLOWER (d = 32: 1.94e9 -> 1.80-1.84e9 evals/s, d = 16: 2.15e9 -> 2.01-2.07e9): the
+  // inputs are 1.3 % of the stall samples already (L2 hits landing behind the wait for P11), and the 49 KB write through
+  // the async proxy competes with the operand fetches of the dW chains for shared-memory bandwidth.
+#ifndef PDEIP_TC_STAGE
+#define PDEIP_TC_STAGE 0
+#endif
+  static constexpr uint32_t STAGE_BYTES = (PDEIP_TC_STAGE && NS == 1) ? 128u * 3u * DP * 4u : 0u;
+  static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, O_STAGE = O_MISC + 128,
+                            TOTAL = O_STAGE + STAGE_BYTES;
+  static_assert(TOTAL <= 227u * 1024u && O_STAGE % 128 == 0, "shared-memory budget");
 };
 
 #ifndef PDEIP_TC_G_CHAIN_EARLY
@@ -327,6 +340,15 @@ __device__ __forceinline__ void put_chunk(uint8_t* tile, uint32_t off, const flo
   q.x = pack2(v[0], v[1]); q.y = pack2(v[2], v[3]); q.z = pack2(v[4], v[5]); q.w = pack2(v[6], v[7]);
   *reinterpret_cast<uint4*>(tile + off) = q;
 }
+// ---- TMA bulk copy (global -> shared, completion on an mbarrier) --------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
 __device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t* r);
 // the chunk to shared memory AND (TS) the same four packed words to the A-operand columns of this thread's TMEM lane
 template <bool TS>
@@ -511,6 +533,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(smem_u32(mbar_p + s), 1);
+    mbar_init(smem_u32(mbar_p + 4), 1);  // input staging (one-slot kernels)
     fence_mbar_init();
   }
   // every operand byte is finite from the start: zero-weight columns multiply whatever the neighbouring band holds
@@ -795,6 +818,20 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
       }
     };
+    // input staging by the TMA unit (one-slot kernels, BLOCK128 point sets: a tile is one contiguous block)
+    constexpr bool kStage = PDEIP_TC_STAGE && NS == 1;
+    const bool use_stage = kStage && a.layout == PDEIP_LAYOUT_BLOCK128 && (reinterpret_cast<uintptr_t>(a.points) & 15u) == 0;
+    const float* const stage = reinterpret_cast<const float*>(sm + S::O_STAGE) + row;  // component c of this row: [c * 128]
+    const uint32_t stage_mbar = smem_u32(mbar_p + 4);
+    uint32_t spar = 0;
+    auto stage_issue = [&](int64_t t) {  // called by ONE thread, after every warp has finished reading the buffer
+      if (t >= n_tiles) return;
+      const int64_t pt = FPM ? (int64_t)((uint32_t)t / fpd) : t;
+      const uint32_t bytes = 512u * (uint32_t)dimw;
+      mbar_expect_tx(stage_mbar, bytes);
+      bulk_g2s(smem_u32(sm + S::O_STAGE), a.points + pt * 128 * dimw, bytes, stage_mbar);
+    };
+    if (use_stage && tid == 0) stage_issue(tile_begin);
     // two separate branches: each slot's loads target its own registers directly (no select on the loaded value)
     auto load_inputs = [&](int s, int64_t t) {
       if (NS == 2 && s == 1) load_into(xin1, t);
@@ -868,8 +905,34 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       };
       constexpr bool kEarlyLoads = true;  // (at d = 32 this used to spill; the shorter life of the input registers fixed that)
 #if PDEIP_TC_L2_PREFETCH
-      if constexpr (ph == 0) load_inputs(s, tile);
+      if constexpr (ph == 0) {
+        if (!use_stage) load_inputs(s, tile);
+      }
 #endif
+      if constexpr (kStage && ph == 0) {
+        if (use_stage) {  // this tile's block has landed in shared memory (bulk copy issued one tile ago, in E7): the
+                          // row is read before the wait for P11, like the global loads of the other layouts
+          if (ok && !mbar_wait(stage_mbar, spar)) {
+            ok = false;
+            atomicExch(status, 1);
+          }
+          spar ^= 1u;
+          const int dir = FPM ? (int)((uint32_t)tile % fpd) : -1;
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const int j = half + 2 * i;
+            const int band = (j / S::XC) < 3 ? (j / S::XC) : 0, cg = j % S::XC;
+            if (band < 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int u = cg * 8 + e;
+                const float val = stage[(band * d + (u < d ? u : 0)) * 128];
+                xin0[i][e] = (FPM && band == 1) ? (u == dir ? 1.f : 0.f) : val;
+              }
+            }
+          }
+        }
+      }
       if constexpr (ph <= 3 || ph == 6 || !kEarlyLoads) wait_gemm();
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
         auto emit = [&](const float (&xin)[NI][8]) {
@@ -1078,7 +1141,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
               const float mkc = mk * cgw;  // FP: each of the d direction rows of a point carries 1/d of the per-point sums
               if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) gt[e] = (valid && cg * 8 + e < d) ? ((NS == 2 && s == 1) ? xin1[i][e] : xin0[i][e]) : 0.f;
+                for (int e = 0; e < 8; ++e) {
+                  const int u = cg * 8 + e;
+                  float val;
+                  if (kStage && use_stage) val = stage[((FPM ? d : 2 * d) + (u < d ? u : 0)) * 128];  // still this tile's block
+                  else val = (NS == 2 && s == 1) ? xin1[i][e] : xin0[i][e];
+                  gt[e] = (valid && u < d) ? val : 0.f;
+                }
               } else if (a.tg.kind == PDEIP_DRIFT_LINEAR || a.tg.kind == PDEIP_DRIFT_GMM) {
                 true_grad_chunk<DP>(a, tp, valid ? p : (int64_t)-1, dimw, cg, gt);
               }
@@ -1103,6 +1172,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         for (int c = 0; c < 2; ++c) load_chunk(At, (AC_C + 2 * half + c) * 128, a2 + 8 * c);
         tm_wait_ld();
         if constexpr (kEarlyLoads) wait_gemm();
+        if constexpr (kStage && l1) {
+          // P6 is committed, so every warp has arrived at the end of E6 (its last read of the staged block, ordered by
+          // the proxy fence of that arrive): the next tile's block may overwrite it, five phases ahead of its E0
+          if (use_stage && tid == 0) stage_issue(tile + tile_stride);
+        }
         tm_ldf<16>(LA + (l1 ? C_ZG0 : C_ZG1) + u16, zg);
         tm_wait_ld();
         float ag[16], cc[16];
@@ -1159,7 +1233,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // proxy fence of epi_arrive waits for every outstanding load of the thread: a load issued late in a phase is a
         // blocking load)
 #if PDEIP_TC_L2_PREFETCH
-        if constexpr (l2) prefetch_inputs(tile + tile_stride);
+        if constexpr (l2) {
+          if (!use_stage) prefetch_inputs(tile + tile_stride);
+        }
 #else
         if constexpr (l2) load_inputs(s, tile + tile_stride);
 #endif

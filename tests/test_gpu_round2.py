@@ -455,7 +455,11 @@ def test_fp_and_boundary_tensor_modes_edge_sizes(cuda, n):
     tol = 1e-2 if n >= 128 else 3e-2  # fewer points than a tile: single-point bf16 rounding, nothing averages
     s1, g1, s2, g2 = res["fp32"]
     t1, h1, t2, h2 = res["tensor"]
-    assert relmax(t1[L.SUM_LOSS], s1[L.SUM_LOSS]) < tol and relmax(h1, g1) < tol
+    # the loss |g|^2 - 2 Laplacian is a cancelling scalar: its error is measured against the size of its two terms
+    terms = abs(float(s1[L.SUM_G2])) + 2.0 * abs(float(s1[L.SUM_D2]))
+    assert abs(float(t1[L.SUM_LOSS] - s1[L.SUM_LOSS])) < tol * terms
+    assert relmax(t1[L.SUM_G2], s1[L.SUM_G2]) < tol and relmax(t1[L.SUM_D2], s1[L.SUM_D2]) < tol
+    assert relmax(h1, g1) < tol
     assert relmax(h2, g2) < tol
 
 
