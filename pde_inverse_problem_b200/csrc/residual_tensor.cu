@@ -99,7 +99,10 @@ struct Cfg {
   static constexpr uint32_t RG_T1 = 512, SZ_T1 = 4 * RG_T1, RG_T2 = 512, SZ_T2 = 6 * RG_T2;
   static constexpr uint32_t O_T0XH = NS * SLOT, O_T0XL = O_T0XH + SZ_T0X, O_T0VH = O_T0XL + SZ_T0X,
                             O_T0VL = O_T0VH + SZ_T0V, O_T1H = O_T0VL + SZ_T0V, O_T1L = O_T1H + SZ_T1,
-                            O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2, O_BIAS = O_T2L + SZ_T2;
+                            O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2,
+                            // Gram tile G = c_g W0 W0^T / 8 ([32 hidden][32 hidden], hi + lo): one-slot kernels only
+                            O_TGH = O_T2L + SZ_T2, O_TGL = O_TGH + (NS == 1 ? SZ_T1 : 0u),
+                            O_BIAS = O_TGL + (NS == 1 ? SZ_T1 : 0u);
   static constexpr uint32_t TP_BYTES = NS == 2 ? 2048 : 4096;
   // PDEIP_TC_STAGE (off by default; round-1 verdict item 8, built and measured in round 2).  One-slot kernels have shared
   // memory to spare: the next tile of a BLOCK128 point set ([3 DP][128] floats, one contiguous block) can be staged by ONE
@@ -501,6 +504,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #define PDEIP_TC_TS 0  // measured (profiles/r02_summary_residual.md): no gain, see C_AOP above
 #endif
   constexpr bool kTS = PDEIP_TC_TS && NS == 1;  // layer-GEMM A operands from TMEM (the two-slot kernel has no columns left)
+#ifndef PDEIP_TC_GRAM
+#define PDEIP_TC_GRAM 1
+#endif
+  // One-slot kernels: zg^_0 = g^ W0 = za^0 (W0 W0^T) c_g / 8 comes out of P5 itself through the Gram tile (hi + lo; the
+  // two-slot kernel has no shared memory for it), so that E6 and E7 run back to back and the P6 hand-off disappears:
+  // 11 GEMM -> epilogue round trips per tile instead of 12, and zg^_0 no longer passes through the bf16 rounding of g^.
+  constexpr bool kGram = PDEIP_TC_GRAM && NS == 1;
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -566,6 +576,15 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       const int r = idx / 32, c = idx % 32;
       put(S::O_T2H, S::O_T2L, S::RG_T2, r, c, r < kOut ? W2[c * kOut + r] : 0.f);
     }
+    if constexpr (kGram) {  // TG[i][j] = (c_g / 8) sum_k W0[k][i] W0[k][j]  (k over the d inputs)
+      const float sc = 0.125f / (float)fpd;
+      for (int idx = tid; idx < 32 * 32; idx += kLaunchThreads) {
+        const int r = idx / 32, c = idx % 32;
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k) acc = fmaf(W0[k * H + r], W0[k * H + c], acc);
+        put(S::O_TGH, S::O_TGL, S::RG_T1, r, c, sc * acc);
+      }
+    }
     for (int j = tid; j < 32; j += kLaunchThreads) {
       bias_s[j] = a.params[sh.b_off(0) + j];
       bias_s[32 + j] = a.params[sh.b_off(1) + j];
@@ -596,6 +615,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     const Desc T0VHK = mk_desc(smem_u32(sm + S::O_T0VH), 128, S::RG_T0V), T0VLK = mk_desc(smem_u32(sm + S::O_T0VL), 128, S::RG_T0V);
     const Desc T1HK = mk_desc(smem_u32(sm + S::O_T1H), 128, S::RG_T1), T1LK = mk_desc(smem_u32(sm + S::O_T1L), 128, S::RG_T1);
     const Desc T2HK = mk_desc(smem_u32(sm + S::O_T2H), 128, S::RG_T2), T2LK = mk_desc(smem_u32(sm + S::O_T2L), 128, S::RG_T2);
+    const Desc TGHK = mk_desc(smem_u32(sm + S::O_TGH), 128, S::RG_T1), TGLK = mk_desc(smem_u32(sm + S::O_TGL), 128, S::RG_T1);
     const Desc T0VHM = mk_desc(smem_u32(sm + S::O_T0VH), S::RG_T0V, 128), T0VLM = mk_desc(smem_u32(sm + S::O_T0VL), S::RG_T0V, 128);
     const Desc T1HM = mk_desc(smem_u32(sm + S::O_T1H), S::RG_T1, 128), T1LM = mk_desc(smem_u32(sm + S::O_T1L), S::RG_T1, 128);
     const Desc T2HM = mk_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128), T2LM = mk_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
@@ -616,6 +636,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     for (int64_t base = tile_begin; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
       for (int ph = 0; ph < 12; ++ph) {
+        if (kGram && ph == 6) continue;  // no P6: its GEMM rides in P5, its dW chain in P7
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
           const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
@@ -663,6 +684,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
                 if constexpr (kTS) mm_bwd_ts<32, S::KV, 1>({TS + C_G}, {AOP}, T0VHM, T0VLM, S::RG_T0V);
                 else mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
+                if constexpr (kGram) mm_fwd<32, 32, 1, true>({TS + C_ZG0}, ZK, {ZC_ZA0 * CH}, TGHK, TGLK);  // zg^_0
                 commit(mb);
               } break;
               case 6: {  // zg^_0 = g^ W0
@@ -679,6 +701,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 if constexpr (kTS) mm_fwd_ts<32, 32, 1, false>({TS + C_ZG1}, {AOP}, T1HK, T1LK);
                 else mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
+                if constexpr (kGram)  // dW0 += g^^T za0 (P6's chain; g^ was written in E6, ordered by E7's arrive)
+                  mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
                 if constexpr (kCChainsEarly) {  // dW1 += c_1^T za1: c_1 is final since E7 (just arrived), za1 since E4
                   const Desc A1M = mk_desc(sb + S::O_A1, S::RG_A, 128);
                   mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
@@ -1171,7 +1195,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #pragma unroll
         for (int c = 0; c < 2; ++c) load_chunk(At, (AC_C + 2 * half + c) * 128, a2 + 8 * c);
         tm_wait_ld();
-        if constexpr (kEarlyLoads) wait_gemm();
+        if constexpr (kEarlyLoads && !(kGram && l1)) wait_gemm();  // kGram: zg^_0 is a P5 result, already waited for in E6
         if constexpr (kStage && l1) {
           // P6 is committed, so every warp has arrived at the end of E6 (its last read of the staged block, ordered by
           // the proxy fence of that arrive): the next tile's block may overwrite it, five phases ahead of its E0
@@ -1279,18 +1303,20 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           put_op<(kTS && l2)>(Z, ((l2 ? ZC_TB : ZC_TA) + 2 * half + c) * 128, LOP + 4 * (2 * half + c), zb + 8 * c);
         TC_PROBE(l2 ? 19 : 20, u16, zb, 16);
       }
-      if constexpr (kTS) tm_wait_st();  // the A-operand columns are complete before the hand-off
-      TC_TRACE(7);
+      if constexpr (!(kGram && ph == 6)) {  // kGram: no hand-off after E6, E7 follows immediately (zg^_0 came out of P5)
+        if constexpr (kTS) tm_wait_st();  // the A-operand columns are complete before the hand-off
+        TC_TRACE(7);
 #ifdef PDEIP_TC_TRACE
-      fence_async_smem();
-      TC_FINE(3);
-      fence_before_sync();
-      TC_FINE(4);
-      asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(kThreads) : "memory");
+        fence_async_smem();
+        TC_FINE(3);
+        fence_before_sync();
+        TC_FINE(4);
+        asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(kThreads) : "memory");
 #else
-      epi_arrive(s);
+        epi_arrive(s);
 #endif
-      TC_TRACE(2);
+        TC_TRACE(2);
+      }
     };
 #define PDEIP_TC_PHASE(PH)                       \
   _Pragma("unroll 1") for (int s_ = 0; s_ < NS; ++s_) phase(IC<PH>{}, s_);
