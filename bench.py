@@ -152,7 +152,11 @@ def build_problem(w, device, seed=1):
         drift_kind = L.DRIFT_MEANFIELD_TABLE if w.get("meanfield") else L.DRIFT_LINEAR
         true = ops.TrueGrad(L.DRIFT_LINEAR, drift)
         cov_half = None
-    model = V_hypothesis(1, [HIDDEN] * LAYERS, d)
+    if w.get("model") == "parametric":  # what the reference's launch scripts train by default (config.yaml:40)
+        from pde_inverse_problem_b200.core.model import V_parametric_GMM, V_parametric_quadratic
+        model = V_parametric_GMM(d, K) if K > 0 else V_parametric_quadratic(d)
+    else:
+        model = V_hypothesis(1, [HIDDEN] * LAYERS, d)
     params = model.init(11, torch.zeros(d, device=device))
     opt = AdamL2(cosine_decay_schedule(1e-2, 20000, 0.001), 1e-3)
     return drift_kind, drift, true, cov_half, model, params, opt
@@ -167,6 +171,7 @@ def measure(name, args, shard, device, local_rank, steps, warmup, with_clocks):
     import torch.distributed as dist
 
     w = dict(WORKLOADS[name])
+    w["model"] = args.model
     strong = "n_total" in w and not args.particles
     if args.particles:
         w["n"] = args.particles
@@ -264,7 +269,11 @@ def measure(name, args, shard, device, local_rank, steps, warmup, with_clocks):
     res_tflops = res_rate * flop_eval / 1e12
     dp, ns = (8, 2) if d <= 8 else ((16, 1) if d <= 16 else (32, 1))
     tensor_int = path == L.PATH_TENSOR and K > 0 and d in (8, 16, 32) and K <= 64
-    if path == L.PATH_TENSOR:
+    parametric = args.model == "parametric"
+    if parametric:  # closed-form model (K5): ~12 K d FLOP per eval, bound by the 3d*4 B it reads per point
+        res_kernel = "gmm_param_residual_kernel (fp32, closed form)" if K > 0 else "quad_param_residual_kernel (fp32, closed form)"
+        per_point, res_traffic_src = None, "not captured for the parametric kernels"
+    elif path == L.PATH_TENSOR:
         res_kernel = "tc::mlp_residual_tc_kernel<%d,%d> (KFP 0T set, tcgen05)" % (dp, ns)
         per_point, res_traffic_src = measured_traffic("mlp_residual_tc<%d,%d>" % (dp, ns))
     else:
@@ -283,7 +292,8 @@ def measure(name, args, shard, device, local_rank, steps, warmup, with_clocks):
                                                   "in the integrator), f32 accumulate / epilogue / state"),
         "data": "synthetic",
         "config": {"workload": f"{name}: {w['name']}", "particles_per_rank": n, "particles_total": n_global,
-                   "d": d, "n_gaussian": K, "n_steps": S, "mlp": f"{d}->{HIDDEN}x{LAYERS}->{OUT}",
+                   "d": d, "n_gaussian": K, "n_steps": S,
+                   "mlp": ("parametric model (closed-form residual)" if parametric else f"{d}->{HIDDEN}x{LAYERS}->{OUT}"),
                    "chunk": cfg.chunk, "residual_path": args.path,
                    "l2_policy": "inputs larger than L2: every chunk's trajectory (%.1f GB) streams through HBM"
                                 % (3 * d * s_emit * cfg.chunk * 4 / 1e9)},
@@ -293,12 +303,16 @@ def measure(name, args, shard, device, local_rank, steps, warmup, with_clocks):
                 "h2d_bytes_per_step": n * 2 * d * 4, "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / e2e_steps * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": res_kernel, "bound": "tensor", "achieved": res_tflops,
-                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
-                     "traffic": res_traffic, "traffic_source": res_traffic_src,
-                     "peak_source": pk["src"] + " bf16 sustained",
-                     "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval,
-                     "frac_of_step": (n * s_emit * flop_eval / (t_dev / steps) / 1e12) / pk["tf_sust"]},
+        "roofline": ({"kernel": res_kernel, "bound": "hbm", "achieved": res_rate * 3 * d * 4 / 1e9, "peak": pk["hbm"],
+                      "unit": "GB/s", "frac": res_rate * 3 * d * 4 / 1e9 / pk["hbm"], "traffic": None,
+                      "traffic_source": res_traffic_src, "peak_source": pk["src"] + " copy bandwidth",
+                      "evals_per_s_per_gpu": res_rate, "bytes_per_eval": 3 * d * 4} if parametric else
+                     {"kernel": res_kernel, "bound": "tensor", "achieved": res_tflops,
+                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tflops / pk["tf_sust"],
+                      "traffic": res_traffic, "traffic_source": res_traffic_src,
+                      "peak_source": pk["src"] + " bf16 sustained",
+                      "evals_per_s_per_gpu": res_rate, "flop_per_eval": flop_eval,
+                      "frac_of_step": (n * s_emit * flop_eval / (t_dev / steps) / 1e12) / pk["tf_sust"]}),
         "kernels": {
             "kl_integrate": {"kernel": ("kl_integrate_tc_kernel (GMM contraction on tcgen05)" if tensor_int
                                         else "kl_integrate_fast_kernel (fp32)"), "bound": "hbm",
@@ -441,6 +455,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.c3 block of the default C5 run")
+    ap.add_argument("--model", default="mlp", choices=["mlp", "parametric"],
+                    help="hypothesis model: mlp = V_hypothesis d->32x2->40 (BASELINE metric), parametric = the closed-form "
+                         "GMM / quadratic model the reference's launch scripts train by default (config.yaml:40)")
     ap.add_argument("--path", default=os.environ.get("PDEIP_BENCH_PATH", "tensor"), choices=["fp32", "tensor"],
                     help="residual kernel: tensor = tcgen05 bf16 GEMM path (rtol 1e-2, default), fp32 = CUDA-core parity path (rtol 1e-5)")
     ap.add_argument("--particles", type=int, default=0, help="override particles per rank")

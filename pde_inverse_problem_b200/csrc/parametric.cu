@@ -466,6 +466,10 @@ static size_t param_smem_bytes(int P, int ntg, int rows_max, int RS) {
   return sizeof(float) * (size_t)(((P + 3) & ~3) + ((ntg + 3) & ~3) + kPNW * per_warp_al);
 }
 
+// parametric_fast.cu: production kernels of the GMM model for d in {4, 8, 16, 32}
+bool gmm_param_fast_ok(int set_kind, const ResidualArgs& a);
+int gmm_param_fast_accumulate(int set_kind, const ResidualArgs& a, int K, cudaStream_t st);
+
 int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& a, int n_gaussian, cudaStream_t st) {
   PDEIP_REQUIRE(a.d >= 1 && a.d <= kPD, PDEIP_ERR_UNSUPPORTED, "parametric residual supports 1 <= d <= %d", kPD);
   const int ntg = true_grad_floats(a.tg, a.d);
@@ -474,6 +478,7 @@ int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& 
     PDEIP_REQUIRE(n_gaussian >= 1 && n_gaussian <= kPK, PDEIP_ERR_UNSUPPORTED, "1 <= n_gaussian <= %d supported", kPK);
     PDEIP_REQUIRE(set_kind == PDEIP_SET_KFP_0T || set_kind == PDEIP_SET_KFP_BOUNDARY, PDEIP_ERR_UNSUPPORTED,
                   "GMM parametric model supports the kinetic point sets only");
+    if (gmm_param_fast_ok(set_kind, a)) return gmm_param_fast_accumulate(set_kind, a, n_gaussian, st);
     const size_t smem = param_smem_bytes(n_gaussian * a.d, ntg, kPK, 64);
     if (set_kind == PDEIP_SET_KFP_0T) {
       auto kern = gmm_param_residual_kernel<PDEIP_SET_KFP_0T>;

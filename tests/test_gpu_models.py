@@ -26,7 +26,7 @@ def _kfp_sets(ops, L, spec, flat, data, tg, gamma, T, cuda):
     return s.cpu().double(), g.cpu().double()
 
 
-@pytest.mark.parametrize("d,K", [(4, 3), (8, 16), (2, 1), (16, 40)])
+@pytest.mark.parametrize("d,K", [(4, 3), (8, 16), (2, 1), (16, 40), (32, 64), (8, 1), (4, 9)])
 def test_gmm_parametric_residual(cuda, d, K):
     """V_parametric of GMM.py:214-234 under kinetic_fokker_planck.py:11-69."""
     ops, L = _ops()
@@ -51,6 +51,42 @@ def test_gmm_parametric_residual(cuda, d, K):
     assert relmax(out["grad"], vmap(grad(V))(x)) < TOL
     assert relmax(out["vHv"], vmap(lambda a, b: torch.dot(b, o_res.hessian_vector_product(V, a, b)))(x, v)) < TOL
     assert relmax(out["laplacian"], vmap(lambda a: torch.diagonal(torch.func.jacfwd(grad(V))(a)).sum())(x)) < TOL
+
+
+@pytest.mark.parametrize("d,K,n", [(8, 16, 128 * 70), (32, 64, 128 * 9), (4, 3, 128 * 33)])
+def test_gmm_parametric_fast_kernel_layouts_and_generic_twin(cuda, d, K, n):
+    """The production GMM-model kernel (parametric_fast.cu: d in {4, 8, 16, 32}) on the three point layouts with grad V_true
+    stored in the points (what the pipeline feeds it), against the generic kernel (PDEIP_NO_FAST_PARAMETRIC) on the same
+    points; ragged tail (n - 37 points) through the AoS layout."""
+    import os
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(d + K)
+    mus = (torch.randn(K, d, generator=g) * 1.5).reshape(-1).to(cuda)
+    pts3 = (torch.randn(n, 3 * d, generator=g) * 1.3).to(cuda)
+    spec = ops.ModelSpec(L.MODEL_GMM, d, n_gaussian=K)
+    tg = ops.TrueGrad(L.DRIFT_IN_POINTS)
+
+    def run(points, layout, n_pts):
+        acc = ops.ResidualAccumulator(spec, device=cuda).begin()
+        acc.accumulate(L.SET_KFP_0T, mus, points, 1.0 / n_pts, coef=0.5, true_grad=tg, layout=layout)
+        acc.accumulate(L.SET_KFP_BOUNDARY, mus, pts3[:1000, : 2 * d].contiguous(), 1e-3, coef=1.0)
+        s, gr = acc.finalize()
+        return s.cpu().double().clone(), gr.cpu().double().clone()
+
+    s_a, g_a = run(pts3, L.LAYOUT_AOS, n)
+    s_s, g_s = run(pts3.t().contiguous(), L.LAYOUT_SOA, n)
+    s_b, g_b = run(pts3.view(n // 128, 128, 3 * d).permute(0, 2, 1).contiguous(), L.LAYOUT_BLOCK128, n)
+    assert torch.equal(s_a, s_s) and torch.equal(g_a, g_s) and torch.equal(s_a, s_b) and torch.equal(g_a, g_b)
+    s_r, g_r = run(pts3[: n - 37].contiguous(), L.LAYOUT_AOS, n - 37)
+    os.environ["PDEIP_NO_FAST_PARAMETRIC"] = "1"
+    try:
+        s_g, g_g = run(pts3, L.LAYOUT_AOS, n)
+        s_gr, g_gr = run(pts3[: n - 37].contiguous(), L.LAYOUT_AOS, n - 37)
+    finally:
+        del os.environ["PDEIP_NO_FAST_PARAMETRIC"]
+    for (s1, g1), (s2, g2) in (((s_a, g_a), (s_g, g_g)), ((s_r, g_r), (s_gr, g_gr))):
+        assert relmax(s1[L.SUM_LOSS], s2[L.SUM_LOSS]) < TOL and relmax(s1[L.SUM_GT], s2[L.SUM_GT]) < TOL
+        assert relmax(g1, g2) < TOL
 
 
 @pytest.mark.parametrize("d", [2, 4, 16])
