@@ -469,6 +469,8 @@ static size_t param_smem_bytes(int P, int ntg, int rows_max, int RS) {
 // parametric_fast.cu: production kernels of the GMM model for d in {4, 8, 16, 32}
 bool gmm_param_fast_ok(int set_kind, const ResidualArgs& a);
 int gmm_param_fast_accumulate(int set_kind, const ResidualArgs& a, int K, cudaStream_t st);
+bool quad_param_fast_ok(int set_kind, const ResidualArgs& a);
+int quad_param_fast_accumulate(int set_kind, const ResidualArgs& a, cudaStream_t st);
 
 int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& a, int n_gaussian, cudaStream_t st) {
   PDEIP_REQUIRE(a.d >= 1 && a.d <= kPD, PDEIP_ERR_UNSUPPORTED, "parametric residual supports 1 <= d <= %d", kPD);
@@ -490,6 +492,7 @@ int param_residual_accumulate(int set_kind, int model_kind, const ResidualArgs& 
       kern<<<grid, kPNW * 32, smem, st>>>(a, n_gaussian);
     }
   } else if (model_kind == PDEIP_MODEL_QUADRATIC) {
+    if (quad_param_fast_ok(set_kind, a)) return quad_param_fast_accumulate(set_kind, a, st);
     const size_t smem = param_smem_bytes(a.d * a.d + a.d, ntg, kPD, 32);
 #define LAUNCH_Q(SET)                                                                                   \
   do {                                                                                                  \

@@ -1,4 +1,5 @@
-// parametric_fast.cu — K5, production kernels: closed-form residual of the parametric GMM model for d in {4, 8, 16, 32}.
+// parametric_fast.cu — K5, production kernels: closed-form residuals of the parametric GMM and quadratic models for
+// d in {4, 8, 16, 32}.
 //
 // Replaces jax.value_and_grad of the KFP loss (methods/consistency_instances/kinetic_fokker_planck.py:33-61) for the
 // model of example_problems/kinetic_fokker_planck_example_GMM.py:214-234 — the model the reference's launch scripts
@@ -282,6 +283,163 @@ static int launch(int set_kind, const ResidualArgs& a, int K, cudaStream_t st) {
   return PDEIP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Quadratic parametric model  V(y) = y.(y W + b)  (example_problems/kinetic_fokker_planck_example_OU.py:209-220,
+// kinetic_mckean_vlasov_example_quadratic.py:205-216): g = (W + W^T) y + b, D_v V = g.v, D_v^2 V = v^T (W + W^T) v.
+//   dW[i][j] += a1_i y_j + a2_i g_j + a3_i v_j,  db_i += a1_i,   a1 = 2 c_g g + beta v,  a2 = 2 c_g y,  a3 = 2 alpha v + beta y
+// (same coefficients as parametric.cu).  One thread = one point, Ws = W + W^T in shared memory, the
+// d x d gradient is reduced over the warp ROW BY ROW with the same transpose-reduce as the GMM kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <int DP, int SET>
+__global__ void __launch_bounds__(Tile<DP>::THREADS, 1) quad_param_fast_kernel(const ResidualArgs a) {
+  constexpr int NT = Tile<DP>::THREADS, NW = NT / 32;
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                  // [DP][DP] = W + W^T
+  float* bs = Ws + DP * DP;          // [DP]
+  float* tp = bs + DP;               // true-gradient parameters (LINEAR / GMM kinds)
+  int ntg = 0;
+  if (a.tg.kind == PDEIP_DRIFT_LINEAR) ntg = DP * DP;
+  else if (a.tg.kind == PDEIP_DRIFT_GMM) ntg = a.tg.n_gaussian * DP;
+  float* acc_base = tp + ((ntg + 3) & ~3);  // [NW][DP * DP + DP]
+  constexpr int ACC = DP * DP + DP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* acc_s = acc_base + warp * ACC;
+  for (int idx = tid; idx < DP * DP; idx += NT) {
+    const int i = idx / DP, j = idx - i * DP;
+    Ws[idx] = a.params[i * DP + j] + a.params[j * DP + i];
+  }
+  for (int i = tid; i < DP; i += NT) bs[i] = a.params[DP * DP + i];
+  for (int i = tid; i < ntg; i += NT) tp[i] = a.tg.params[i];
+  for (int idx = tid; idx < NW * ACC; idx += NT) acc_base[idx] = 0.f;
+  __syncthreads();
+
+  const int dimw = 2 * DP + (a.tg.kind == PDEIP_DRIFT_IN_POINTS ? DP : 0);
+  const int64_t cstride = comp_stride(a.layout, a.n_points);
+  constexpr int SH = 32 / DP;
+  const int comp = lane / SH;
+  const bool writer = (lane % SH) == 0;
+  float sums[PDEIP_NUM_SUMS];
+#pragma unroll
+  for (int k = 0; k < PDEIP_NUM_SUMS; ++k) sums[k] = 0.f;
+
+  const int64_t n_tiles = (a.n_points + NT - 1) / NT;
+#pragma unroll 1
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p = tile * NT + tid;
+    const bool valid = p < a.n_points;
+    const float wt = valid ? a.weight : 0.f;
+    const float* pb = a.points + point_base(a.layout, valid ? p : 0, dimw);
+    float y[DP], v[DP], g[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      y[i] = __ldg(pb + i * cstride);
+      v[i] = __ldg(pb + (DP + i) * cstride);
+    }
+    float D1 = 0.f, D2 = 0.f, g2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      const float4* row = reinterpret_cast<const float4*>(Ws + i * DP);
+      float s = bs[i], h = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < DP / 4; ++j4) {
+        const float4 t = row[j4];
+        s = fmaf(t.x, y[4 * j4], fmaf(t.y, y[4 * j4 + 1], fmaf(t.z, y[4 * j4 + 2], fmaf(t.w, y[4 * j4 + 3], s))));
+        h = fmaf(t.x, v[4 * j4], fmaf(t.y, v[4 * j4 + 1], fmaf(t.z, v[4 * j4 + 2], fmaf(t.w, v[4 * j4 + 3], h))));
+      }
+      g[i] = s;
+      D1 = fmaf(s, v[i], D1);
+      D2 = fmaf(h, v[i], D2);
+      g2 = fmaf(s, s, g2);
+    }
+    float alpha, beta, cg;
+    if (SET == PDEIP_SET_KFP_0T) {
+      const float gamma = a.coef;
+      alpha = -2.f * wt; beta = 2.f * gamma * wt; cg = wt;
+      float gt[DP];
+      if (a.tg.kind == PDEIP_DRIFT_IN_POINTS) {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) gt[i] = __ldg(pb + (2 * DP + i) * cstride);
+      } else {
+        true_grad_thread(a.tg, tp, DP, y, gt);
+      }
+      float gt2 = 0.f, gd2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) {
+        gt2 = fmaf(gt[i], gt[i], gt2);
+        const float df = gt[i] - g[i];
+        gd2 = fmaf(df, df, gd2);
+      }
+      sums[PDEIP_SUM_G2] += wt * g2;
+      sums[PDEIP_SUM_D2] += wt * D2;
+      sums[PDEIP_SUM_D1] += wt * D1;
+      sums[PDEIP_SUM_GTRUE2] += wt * gt2;
+      sums[PDEIP_SUM_GT] += wt * gd2;
+      sums[PDEIP_SUM_LOSS] += wt * (g2 - 2.f * D2 + 2.f * gamma * D1 + gt2);
+    } else {
+      alpha = 0.f; beta = a.coef * wt; cg = 0.f;
+      sums[PDEIP_SUM_BOUNDARY] += wt * a.coef * D1;
+      sums[PDEIP_SUM_LOSS] += wt * a.coef * D1;
+    }
+    const float c2g = 2.f * cg, a2c = 2.f * alpha;
+    float a1[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) a1[i] = fmaf(c2g, g[i], beta * v[i]);
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {  // row i of dW: a1_i y + a2_i g + a3_i v
+      const float a2i = c2g * y[i], a3i = fmaf(a2c, v[i], beta * y[i]);
+      float t[DP];
+#pragma unroll
+      for (int j = 0; j < DP; ++j) t[j] = fmaf(a1[i], y[j], fmaf(a2i, g[j], a3i * v[j]));
+      const float tot = transpose_reduce<DP>(t, lane);
+      if (writer) acc_s[i * DP + comp] += tot;
+    }
+    {
+      const float tot = transpose_reduce<DP>(a1, lane);  // db
+      if (writer) acc_s[DP * DP + comp] += tot;
+    }
+  }
+  __syncthreads();
+  float* part = a.ws + (int64_t)blockIdx.x * a.pstride;
+  for (int idx = tid; idx < ACC; idx += NT) {
+    float s = 0.f;
+    for (int w = 0; w < NW; ++w) s += acc_base[w * ACC + idx];
+    part[idx] += s;  // flat layout of the quadratic model: W [d][d] row-major, then b [d]
+  }
+  __syncthreads();
+  float* red = acc_base;
+#pragma unroll
+  for (int k = 0; k < PDEIP_NUM_SUMS; ++k) {
+    const float s = warp_sum(sums[k]);
+    if (lane == 0) red[warp * PDEIP_NUM_SUMS + k] = s;
+  }
+  __syncthreads();
+  if (tid < PDEIP_NUM_SUMS) {
+    float s = 0.f;
+    for (int w = 0; w < NW; ++w) s += red[w * PDEIP_NUM_SUMS + tid];
+    part[ACC + tid] += s;
+  }
+}
+
+template <int DP>
+static int launch_quad(int set_kind, const ResidualArgs& a, cudaStream_t st) {
+  constexpr int NT = Tile<DP>::THREADS, NW = NT / 32;
+  const int ntg = true_grad_floats(a.tg, a.d);
+  const size_t smem = sizeof(float) * ((size_t)DP * DP + DP + ((ntg + 3) & ~3) + (size_t)NW * (DP * DP + DP) + NW * PDEIP_NUM_SUMS);
+  PDEIP_REQUIRE(smem <= 227 * 1024, PDEIP_ERR_UNSUPPORTED, "parametric quadratic kernel needs %zu B of shared memory", smem);
+  const int grid = residual_grid();
+  if (set_kind == PDEIP_SET_KFP_0T) {
+    auto kern = quad_param_fast_kernel<DP, PDEIP_SET_KFP_0T>;
+    PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, st>>>(a);
+  } else {
+    auto kern = quad_param_fast_kernel<DP, PDEIP_SET_KFP_BOUNDARY>;
+    PDEIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, st>>>(a);
+  }
+  PDEIP_LAUNCH_OK();
+  return PDEIP_OK;
+}
+
 }  // namespace pfast
 
 // true if (d, set) is served by the production kernel; the caller falls back to parametric.cu otherwise
@@ -296,6 +454,21 @@ int gmm_param_fast_accumulate(int set_kind, const ResidualArgs& a, int K, cudaSt
     case 8: return pfast::launch<8>(set_kind, a, K, st);
     case 16: return pfast::launch<16>(set_kind, a, K, st);
     default: return pfast::launch<32>(set_kind, a, K, st);
+  }
+}
+
+}  // namespace pdeip
+
+namespace pdeip {
+
+bool quad_param_fast_ok(int set_kind, const ResidualArgs& a) { return gmm_param_fast_ok(set_kind, a); }
+
+int quad_param_fast_accumulate(int set_kind, const ResidualArgs& a, cudaStream_t st) {
+  switch (a.d) {
+    case 4: return pfast::launch_quad<4>(set_kind, a, st);
+    case 8: return pfast::launch_quad<8>(set_kind, a, st);
+    case 16: return pfast::launch_quad<16>(set_kind, a, st);
+    default: return pfast::launch_quad<32>(set_kind, a, st);
   }
 }
 

@@ -89,7 +89,43 @@ def test_gmm_parametric_fast_kernel_layouts_and_generic_twin(cuda, d, K, n):
         assert relmax(g1, g2) < TOL
 
 
-@pytest.mark.parametrize("d", [2, 4, 16])
+@pytest.mark.parametrize("d,n", [(4, 128 * 50), (8, 128 * 21), (16, 128 * 30), (32, 128 * 7)])
+def test_quadratic_parametric_fast_kernel_layouts_and_generic_twin(cuda, d, n):
+    """The production quadratic-model kernel (parametric_fast.cu) on the three point layouts with grad V_true stored in
+    the points, against the generic kernel (PDEIP_NO_FAST_PARAMETRIC); ragged tail through the AoS layout."""
+    import os
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(3 * d)
+    flat = torch.cat([(torch.randn(d, d, generator=g) / d).reshape(-1), 0.2 * torch.randn(d, generator=g)]).to(cuda)
+    pts3 = (torch.randn(n, 3 * d, generator=g) * 1.1).to(cuda)
+    spec = ops.ModelSpec(L.MODEL_QUADRATIC, d)
+    tg = ops.TrueGrad(L.DRIFT_IN_POINTS)
+
+    def run(points, layout, n_pts):
+        acc = ops.ResidualAccumulator(spec, device=cuda).begin()
+        acc.accumulate(L.SET_KFP_0T, flat, points, 1.0 / n_pts, coef=0.7, true_grad=tg, layout=layout)
+        acc.accumulate(L.SET_KFP_BOUNDARY, flat, pts3[:900, : 2 * d].contiguous(), 1.0 / 900, coef=-1.0)
+        s, gr = acc.finalize()
+        return s.cpu().double().clone(), gr.cpu().double().clone()
+
+    s_a, g_a = run(pts3, L.LAYOUT_AOS, n)
+    s_s, g_s = run(pts3.t().contiguous(), L.LAYOUT_SOA, n)
+    s_b, g_b = run(pts3.view(n // 128, 128, 3 * d).permute(0, 2, 1).contiguous(), L.LAYOUT_BLOCK128, n)
+    assert torch.equal(s_a, s_s) and torch.equal(g_a, g_s) and torch.equal(s_a, s_b) and torch.equal(g_a, g_b)
+    s_r, g_r = run(pts3[: n - 55].contiguous(), L.LAYOUT_AOS, n - 55)
+    os.environ["PDEIP_NO_FAST_PARAMETRIC"] = "1"
+    try:
+        s_g, g_g = run(pts3, L.LAYOUT_AOS, n)
+        s_gr, g_gr = run(pts3[: n - 55].contiguous(), L.LAYOUT_AOS, n - 55)
+    finally:
+        del os.environ["PDEIP_NO_FAST_PARAMETRIC"]
+    for (s1, g1), (s2, g2) in (((s_a, g_a), (s_g, g_g)), ((s_r, g_r), (s_gr, g_gr))):
+        assert relmax(s1[L.SUM_LOSS], s2[L.SUM_LOSS]) < TOL and relmax(s1[L.SUM_GT], s2[L.SUM_GT]) < TOL
+        assert relmax(s1[L.SUM_BOUNDARY], s2[L.SUM_BOUNDARY]) < TOL
+        assert relmax(g1, g2) < TOL
+
+
+@pytest.mark.parametrize("d", [2, 4, 8, 16, 32])
 def test_quadratic_parametric_residual(cuda, d):
     """V_parametric of OU.py:209-220 under kinetic_fokker_planck.py:11-69; KAT-4: W = F/2, b = 0 -> ground truth 0."""
     ops, L = _ops()
