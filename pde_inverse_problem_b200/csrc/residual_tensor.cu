@@ -144,7 +144,7 @@ constexpr int kLaunchThreads = 384;
 // (epilogue, third group) register budgets after setmaxnreg (the kernel is compiled and launched at 168)
 #ifndef PDEIP_TC_REGS1_EPI
 #define PDEIP_TC_REGS1_EPI 232
-#define PDEIP_TC_REGS1_MMA 24
+#define PDEIP_TC_REGS1_MMA 40
 #endif
 #ifndef PDEIP_TC_REGS2_EPI
 #define PDEIP_TC_REGS2_EPI 208
@@ -211,6 +211,21 @@ __device__ __forceinline__ Desc mk_desc(uint32_t saddr, uint32_t lbo_bytes, uint
   d.lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
   d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // descriptor version 1 (bit 46)
   return d;
+}
+// the same descriptor from base16 = (1024-aligned shared-window address) >> 4 and a compile-time byte offset: ONE add
+// (shared addresses stay below 2^18, so the 14-bit address field cannot carry into the LBO field)
+__device__ __forceinline__ Desc mk_desc16(uint32_t base16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  Desc d;
+  d.lo = base16 + ((off_bytes >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16));
+  d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return d;
+}
+// value the compiler can neither hoist out of a loop nor keep live across it (the MMA warp runs on a small register
+// budget after setmaxnreg: everything it needs is re-derived from two bases inside each phase)
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
 }
 __device__ __forceinline__ void mma(uint32_t d_tmem, Desc a, uint32_t a_adv, Desc b, uint32_t b_adv, uint32_t idesc,
                                     uint32_t accumulate) {
@@ -610,15 +625,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs<NS>::kMma));
   }
   if (is_mma_warp) {
-    // weights: K-major views (LBO = 128: next 8 columns, SBO = row-group bytes) and transposed views
-    const Desc T0XHK = mk_desc(smem_u32(sm + S::O_T0XH), 128, S::RG_T0X), T0XLK = mk_desc(smem_u32(sm + S::O_T0XL), 128, S::RG_T0X);
-    const Desc T0VHK = mk_desc(smem_u32(sm + S::O_T0VH), 128, S::RG_T0V), T0VLK = mk_desc(smem_u32(sm + S::O_T0VL), 128, S::RG_T0V);
-    const Desc T1HK = mk_desc(smem_u32(sm + S::O_T1H), 128, S::RG_T1), T1LK = mk_desc(smem_u32(sm + S::O_T1L), 128, S::RG_T1);
-    const Desc T2HK = mk_desc(smem_u32(sm + S::O_T2H), 128, S::RG_T2), T2LK = mk_desc(smem_u32(sm + S::O_T2L), 128, S::RG_T2);
-    const Desc TGHK = mk_desc(smem_u32(sm + S::O_TGH), 128, S::RG_T1), TGLK = mk_desc(smem_u32(sm + S::O_TGL), 128, S::RG_T1);
-    const Desc T0VHM = mk_desc(smem_u32(sm + S::O_T0VH), S::RG_T0V, 128), T0VLM = mk_desc(smem_u32(sm + S::O_T0VL), S::RG_T0V, 128);
-    const Desc T1HM = mk_desc(smem_u32(sm + S::O_T1H), S::RG_T1, 128), T1LM = mk_desc(smem_u32(sm + S::O_T1L), S::RG_T1, 128);
-    const Desc T2HM = mk_desc(smem_u32(sm + S::O_T2H), S::RG_T2, 128), T2LM = mk_desc(smem_u32(sm + S::O_T2L), S::RG_T2, 128);
+    // Descriptors are NOT kept in registers across the tile loop (18 weight views + 8 slot views would not fit the
+    // budget left by setmaxnreg and were spilled: 75 LDL / STL in front of the MMAs of every phase, profiles/
+    // r02_summary_residual.md): each phase re-derives the few it needs from the shared-memory base with one add each.
+    const uint32_t sm16 = smem_u32(sm) >> 4;
     constexpr uint32_t CH = 128;  // bytes per chunk (8 operand columns)
     uint32_t dw_started = 0;      // becomes 1 after the first tile's P3..P5 background GEMMs
     // dW chains whose operands are final before the tail are issued where the tensor pipe idles (P6..P8: 1-2 MMAs per
@@ -639,13 +649,23 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         if (kGram && ph == 6) continue;  // no P6: its GEMM rides in P5, its dW chain in P7
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
-          const uint32_t TS = TB + C_SLOT0 + (uint32_t)s * SLOT_COLS;
+          const uint32_t w16 = opaque(sm16), b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4));
+          const uint32_t TBo = opaque(TB);
+          const uint32_t TS = TBo + C_SLOT0 + (uint32_t)s * SLOT_COLS;
           const uint32_t mb = smem_u32(mbar_p + s);
-          const uint32_t AOP = TB + C_AOP;  // A-operand columns (kTS)
-          const Desc XK = mk_desc(sb + S::O_X, 128, S::RG_X), A1K = mk_desc(sb + S::O_A1, 128, S::RG_A),
-                     A2K = mk_desc(sb + S::O_A2, 128, S::RG_A), ZK = mk_desc(sb + S::O_Z, 128, S::RG_Z);
-          const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
+          const uint32_t AOP = TBo + C_AOP;  // A-operand columns (kTS)
+          // weights: K-major views (LBO = 128: next 8 columns, SBO = row-group bytes) and transposed views
+          const Desc T0XHK = mk_desc16(w16, S::O_T0XH, 128, S::RG_T0X), T0XLK = mk_desc16(w16, S::O_T0XL, 128, S::RG_T0X);
+          const Desc T0VHK = mk_desc16(w16, S::O_T0VH, 128, S::RG_T0V), T0VLK = mk_desc16(w16, S::O_T0VL, 128, S::RG_T0V);
+          const Desc T1HK = mk_desc16(w16, S::O_T1H, 128, S::RG_T1), T1LK = mk_desc16(w16, S::O_T1L, 128, S::RG_T1);
+          const Desc T2HK = mk_desc16(w16, S::O_T2H, 128, S::RG_T2), T2LK = mk_desc16(w16, S::O_T2L, 128, S::RG_T2);
+          const Desc TGHK = mk_desc16(w16, S::O_TGH, 128, S::RG_T1), TGLK = mk_desc16(w16, S::O_TGL, 128, S::RG_T1);
+          const Desc T0VHM = mk_desc16(w16, S::O_T0VH, S::RG_T0V, 128), T0VLM = mk_desc16(w16, S::O_T0VL, S::RG_T0V, 128);
+          const Desc T1HM = mk_desc16(w16, S::O_T1H, S::RG_T1, 128), T1LM = mk_desc16(w16, S::O_T1L, S::RG_T1, 128);
+          const Desc T2HM = mk_desc16(w16, S::O_T2H, S::RG_T2, 128), T2LM = mk_desc16(w16, S::O_T2L, S::RG_T2, 128);
+          const Desc XK = mk_desc16(b16, S::O_X, 128, S::RG_X), A1K = mk_desc16(b16, S::O_A1, 128, S::RG_A),
+                     A2K = mk_desc16(b16, S::O_A2, 128, S::RG_A), ZK = mk_desc16(b16, S::O_Z, 128, S::RG_Z);
+          const Desc XM = mk_desc16(b16, S::O_X, S::RG_X, 128), ZM = mk_desc16(b16, S::O_Z, S::RG_Z, 128);
           TC_TRACE_DECL_MMA;
           mma_wait_operands(s);
           if (elect_one()) {
@@ -694,7 +714,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #if PDEIP_TC_G_CHAIN_EARLY
                 // dW0 += g^^T za0: both operands are final since E6 / E5, and the tensor pipe idles through P6..P8 (1-2
                 // MMAs per phase) while the tail P9..P11 is bound by it: issued here, behind this slot's commit
-                mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
 #endif
               } break;
               case 7: {  // zg^_1 = ag^_1 W1  (operand in the a1 band)
@@ -702,10 +722,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 else mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
                 if constexpr (kGram)  // dW0 += g^^T za0 (P6's chain; g^ was written in E6, ordered by E7's arrive)
-                  mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
                 if constexpr (kCChainsEarly) {  // dW1 += c_1^T za1: c_1 is final since E7 (just arrived), za1 since E4
-                  const Desc A1M = mk_desc(sb + S::O_A1, S::RG_A, 128);
-                  mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+                  const Desc A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128);
+                  mm_outer<32>(TBo + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
                 }
               } break;
               case 8: {  // ug^ = ag^_2 W2
@@ -713,8 +733,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 else mm_fwd<32, OP, 1, false>({TS + C_UG}, A2K, {AC_A1 * CH}, T2HK, T2LK);
                 commit(mb);
                 if constexpr (kCChainsEarly) {  // dW2 += c_2^T za2: c_2 is final since E8 (just arrived), za2 since E3
-                  const Desc A2M = mk_desc(sb + S::O_A2, S::RG_A, 128);
-                  mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+                  const Desc A2M = mk_desc16(b16, S::O_A2, S::RG_A, 128);
+                  mm_outer<OP>(TBo + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
                 }
               } break;
               case 9: {  // ab_2 = s0 W2^T, aa2 again;  dW2 += t2^T s0 + c_2^T za2
@@ -736,12 +756,12 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 commit(mb);
               } break;
               default: {  // dW0 += x_hi^T zbar0'' (+ x_lo^T zbar0'' if PDEIP_TC_XLO_DW) + g^^T za0
-                mm_outer<32>(TB + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                mm_outer<32>(TBo + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #ifdef PDEIP_TC_XLO_DW  // measured: +2 % time, no visible effect on the gradient error (x_lo = x - bf16(x) averages out)
-                mm_outer<32>(TB + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                mm_outer<32>(TBo + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #endif
 #if !PDEIP_TC_G_CHAIN_EARLY
-                mm_outer<32>(TB + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
 #endif
                 commit(mb);  // the next tile's E0 overwrites the x | v bands
               } break;
@@ -755,30 +775,30 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         if (ph == 3 || ph == 4 || ph == 5 || ph == 9 || ph == 10) {
 #pragma unroll 1
           for (int s = 0; s < NS; ++s) {
-            const uint32_t sb = smem_u32(sm) + (uint32_t)s * S::SLOT;
-            const Desc XM = mk_desc(sb + S::O_X, S::RG_X, 128), A1M = mk_desc(sb + S::O_A1, S::RG_A, 128),
-                       A2M = mk_desc(sb + S::O_A2, S::RG_A, 128), ZM = mk_desc(sb + S::O_Z, S::RG_Z, 128);
+            const uint32_t b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4)), TBo = opaque(TB);
+            const Desc XM = mk_desc16(b16, S::O_X, S::RG_X, 128), A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128),
+                       A2M = mk_desc16(b16, S::O_A2, S::RG_A, 128), ZM = mk_desc16(b16, S::O_Z, S::RG_Z, 128);
             const uint32_t acc_first = (dw_started | (uint32_t)s) ? 1u : 0u;
             if (elect_one()) {
               switch (ph) {
                 case 3:  // dW2 += a1_2^T s1v
-                  mm_outer<OP>(TB + C_DW2, A2M, AC_A1 * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+                  mm_outer<OP>(TBo + C_DW2, A2M, AC_A1 * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, acc_first);
                   break;
                 case 4:  // dW1 += a1_1^T zbar1'
-                  mm_outer<32>(TB + C_DW1, A1M, AC_A1 * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, acc_first);
+                  mm_outer<32>(TBo + C_DW1, A1M, AC_A1 * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, acc_first);
                   break;
                 case 5:  // dW0 += v^T zbar1''
-                  mm_outer<32>(TB + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_V * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, acc_first);
                   break;
                 case 9:  // dW2 += t2^T s0 + c_2^T za2
-                  mm_outer<OP>(TB + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                  mm_outer<OP>(TBo + C_DW2, A2M, AC_T * CH, S::RG_A, ZM, ZC_TA * CH, S::RG_Z, 1u);
                   if constexpr (!kCChainsEarly)
-                    mm_outer<OP>(TB + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
+                    mm_outer<OP>(TBo + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
                   break;
                 default:  // dW1 += t1^T zbar0' + c_1^T za1
-                  mm_outer<32>(TB + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
+                  mm_outer<32>(TBo + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
                   if constexpr (!kCChainsEarly)
-                    mm_outer<32>(TB + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
+                    mm_outer<32>(TBo + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
                   break;
               }
             }

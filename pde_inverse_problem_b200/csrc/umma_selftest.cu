@@ -192,3 +192,89 @@ extern "C" int pdeip_debug_tmem_bw(int n_warps, int reps, long long* out_host) {
   cudaFree(d);
   return PDEIP_OK;
 }
+
+// ---- tcgen05.mma cost probe: `reps` MMAs of shape M x N x 16 (bf16, fp32 accumulate) issued back to back by one thread,
+// cycles from the first issue to the completion of the commit.  variant bit 0: A operand from TMEM instead of shared
+// memory; bit 1: M = 64 instead of 128; bit 2: rotate over 4 accumulators (independent MMAs) instead of one chain;
+// bit 3: B through the MN-major (transposed) view; bit 4: rotate over 4 A tiles; bit 5: rotate over 4 B tiles;
+// bit 6: pairs (A0 B0)(A0 B1)(A1 B0)(A1 B1): consecutive MMAs share their A operand. ----
+namespace pdeip {
+constexpr int kCostATile = 128 * 16 * 2, kCostBTile = 256 * 16 * 2;
+__global__ void __launch_bounds__(128) umma_cost_kernel(int N, int reps, int variant, long long* out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 512);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_u32(&mbar), 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < 4 * (kCostATile + kCostBTile) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0, 0x3f803f80u);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  if (warp == 0 && umma::elect_one()) {
+    const bool ts = variant & 1, m64 = variant & 2, rot = variant & 4, bmn = variant & 8;
+    const bool rota = variant & 16, rotb = variant & 32, pairs = variant & 64;
+    const uint32_t at = umma::smem_u32(sm), bt = at + 4 * kCostATile;
+    uint32_t idesc = umma::make_idesc(N, 0, bmn ? 1 : 0);
+    if (m64) idesc = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(64 >> 4) << 24);
+    const uint32_t ncol = rot ? (uint32_t)N : 0u;
+    const uint32_t d0 = tbase, d1 = tbase + ncol, d2 = tbase + 2 * ncol, d3 = tbase + 3 * ncol;
+    uint32_t ta[4];
+    uint64_t ad[4], bd[4];
+    for (int j = 0; j < 4; ++j) {
+      const int ja = pairs ? (j >> 1) : (rota ? j : 0), jb = pairs ? (j & 1) : (rotb ? j : 0);
+      ta[j] = tbase + 480 + 8 * ja;
+      ad[j] = umma::make_desc(at + ja * kCostATile, 128u, 256u);  // [128][16] K-major: 2 chunks per row group
+      bd[j] = bmn ? umma::make_desc(bt + jb * kCostBTile, (uint32_t)(N / 8) * 128u, 128u) : umma::make_desc(bt + jb * kCostBTile, 128u, 256u);
+    }
+    const long long t0 = clock64();
+    if (ts) {
+#pragma unroll 1
+      for (int r = 0; r < reps; r += 8) {
+        umma::mma_bf16_ts(d0, ta[0], bd[0], idesc, 1u); umma::mma_bf16_ts(d1, ta[1], bd[1], idesc, 1u);
+        umma::mma_bf16_ts(d2, ta[2], bd[2], idesc, 1u); umma::mma_bf16_ts(d3, ta[3], bd[3], idesc, 1u);
+        umma::mma_bf16_ts(d0, ta[0], bd[0], idesc, 1u); umma::mma_bf16_ts(d1, ta[1], bd[1], idesc, 1u);
+        umma::mma_bf16_ts(d2, ta[2], bd[2], idesc, 1u); umma::mma_bf16_ts(d3, ta[3], bd[3], idesc, 1u);
+      }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < reps; r += 8) {
+        umma::mma_bf16(d0, ad[0], bd[0], idesc, 1u); umma::mma_bf16(d1, ad[1], bd[1], idesc, 1u);
+        umma::mma_bf16(d2, ad[2], bd[2], idesc, 1u); umma::mma_bf16(d3, ad[3], bd[3], idesc, 1u);
+        umma::mma_bf16(d0, ad[0], bd[0], idesc, 1u); umma::mma_bf16(d1, ad[1], bd[1], idesc, 1u);
+        umma::mma_bf16(d2, ad[2], bd[2], idesc, 1u); umma::mma_bf16(d3, ad[3], bd[3], idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    umma::commit(umma::smem_u32(&mbar));
+    umma::mbar_wait(umma::smem_u32(&mbar), 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;  // issue time
+    out[1] = t2 - t0;  // until all complete
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+}  // namespace pdeip
+
+extern "C" int pdeip_debug_umma_cost(int N, int reps, int variant, long long* out_host) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return PDEIP_ERR_CUDA;
+  cudaMemset(d, 0, 16);
+  const int smem = 4 * (pdeip::kCostATile + pdeip::kCostBTile) + 1024;
+  cudaFuncSetAttribute(pdeip::umma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pdeip::umma_cost_kernel<<<1, 128, smem>>>(N, reps, variant, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(d); return PDEIP_ERR_CUDA; }
+  cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return PDEIP_OK;
+}
