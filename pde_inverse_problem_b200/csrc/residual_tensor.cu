@@ -66,15 +66,16 @@ constexpr uint32_t C_ZG0 = C_R + 64, C_ZG1 = C_R + 96, C_UG = C_R + 48;     // P
 constexpr uint32_t C_AB2 = C_R + 16, C_AA2R = C_R + 96;                     // P9
 constexpr uint32_t C_AB1 = C_R + 48, C_AA1R = C_R + 96;                     // P10
 
-// PDEIP_TC_TS (off by default; round-1 verdict item 1a, built and measured in round 2).  One-slot kernels (d > 8) use 312
-// of the 512 TMEM columns: the next 48 can hold the A OPERAND of the layer GEMMs (tcgen05.mma [d], [a_tmem], b_desc:
-// lane = point row, column c = the bf16 pair (k = 2c, 2c + 1) of that row): the epilogue thread that packs an 8-unit
-// chunk for the shared-memory tile (which the batch-reduced dW GEMMs still read through the transposed view) also stores
-// the same four words to TMEM.  Correct (tests/test_gpu_umma.py::test_a_operand_from_tensor_memory, all tensor-path
-// tests), but it does NOT shorten the GEMM phases: the phase trace shows the same 60-75 cycles per 128 x 32..48 x 16 MMA
-// with the A operand in TMEM as in shared memory (P1: 8 MMAs in 527 cycles either way), i.e. the instruction is paced by
-// its accumulator traffic (a 16 KB fp32 tile read and written per K = 16 step), not by the A fetch, and the extra
-// tcgen05.st + wait::st and 400 B more spills cost 11 % at d = 32 (1.94e9 -> 1.72e9 evals/s).
+// PDEIP_TC_TS (on; round-1 verdict item 1a).  One-slot kernels (d > 8) use 312 of the 512 TMEM columns: the next 48 hold
+// the A OPERAND of the layer GEMMs (tcgen05.mma [d], [a_tmem], b_desc: lane = point row, column c = the bf16 pair
+// (k = 2c, 2c + 1) of that row): the epilogue thread that packs an 8-unit chunk for the shared-memory tile (which the
+// batch-reduced dW GEMMs still read through the transposed view) also stores the same four words to TMEM.
+// Cost model measured with tools/umma_cost.py (profiles/r02_umma_cost.txt): a 128 x N x 16 MMA with both operands in
+// shared memory costs (4 KB of A + 32 N bytes of B) / 128 B per clock + 4 = 44 / 47 cycles at N = 32 / 48 (shared-memory
+// operand bandwidth, whatever the accumulator or the operand rotation); with A in TMEM it costs N / 2 + 2 = 18 / 27
+// cycles (the math).  The first measurement of this switch saw no gain because the MMA warp itself was the bottleneck
+// (24 registers after setmaxnreg: 75 spill instructions and R2UR chains in front of the MMAs of every phase); with the
+// MMA warp on the uniform datapath the GEMM phases shorten by ~100 cycles each: d = 32 2.055e9 -> 2.24e9 evals/s.
 constexpr uint32_t C_AOP = C_SLOT0 + SLOT_COLS;  // [312, 360): columns = 4 x (chunk index within the operand)
 
 // ---- shared memory ---------------------------------------------------------------------------------------------
@@ -165,14 +166,17 @@ struct IC {
   static constexpr int value = V;
 };
 
-// PDEIP_TC_TRACE builds: clock stamps of one steady-state tile round of CTA 0: trace[(ph * 2 + slot) * 8 + k],
+// PDEIP_TC_TRACE builds: clock stamps SUMMED over kTraceTiles steady-state tile rounds of CTA 0 (differences of the sums
+// are sums of the differences; the tool divides): trace[(ph * 2 + slot) * 8 + k],
 // k = 0 epilogue wait start, 1 wait end, 2 arrive;  4 MMA warp operands ready, 5 fast GEMMs issued, 6 all issued
 #ifdef PDEIP_TC_TRACE
-#define TC_TRACE(k) do { if (trace_on) trace[(ph * 2 + s) * 8 + (k)] = clock64(); } while (0)
-#define TC_FINE(k) do { if (trace_on && ph == 4) trace[240 + s * 8 + (k)] = clock64(); } while (0)
+constexpr int kTraceTiles = 64;
+// (fire-and-forget reductions: a load-add-store would stall the stamped thread on the load)
+#define TC_TRACE(k) do { if (trace_on) atomicAdd(reinterpret_cast<unsigned long long*>(trace) + (ph * 2 + s) * 8 + (k), (unsigned long long)clock64()); } while (0)
+#define TC_FINE(k) do { if (trace_on && ph == 4) atomicAdd(reinterpret_cast<unsigned long long*>(trace) + 240 + s * 8 + (k), (unsigned long long)clock64()); } while (0)
 #define TC_TRACE_DECL_MMA                                                     \
   long long* trace = reinterpret_cast<long long*>(status) + 512;              \
-  const bool trace_on = blockIdx.x == 0 && base == (int64_t)50 * tile_stride
+  const bool trace_on = blockIdx.x == 0 && base >= tile_begin + (int64_t)16 * tile_stride && base < tile_begin + (int64_t)(16 + kTraceTiles) * tile_stride
 #else
 #define TC_TRACE(k) do { } while (0)
 #define TC_FINE(k) do { } while (0)
@@ -516,7 +520,7 @@ template <int DP, int NS, int MODE>
 __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(const ResidualArgs a, int* status) {
   constexpr bool BND = MODE == kModeBnd, FPM = MODE == kModeFp0T;
 #ifndef PDEIP_TC_TS
-#define PDEIP_TC_TS 0  // measured (profiles/r02_summary_residual.md): no gain, see C_AOP above
+#define PDEIP_TC_TS 1  // see C_AOP above
 #endif
   constexpr bool kTS = PDEIP_TC_TS && NS == 1;  // layer-GEMM A operands from TMEM (the two-slot kernel has no columns left)
 #ifndef PDEIP_TC_GRAM
@@ -929,7 +933,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
 #ifdef PDEIP_TC_TRACE
       long long* trace = reinterpret_cast<long long*>(status) + 512;
-      const bool trace_on = blockIdx.x == 0 && tid == 0 && base == (int64_t)50 * tile_stride;
+      const bool trace_on = blockIdx.x == 0 && tid == 0 && base >= tile_begin + (int64_t)16 * tile_stride &&
+                            base < tile_begin + (int64_t)(16 + kTraceTiles) * tile_stride;
 #endif
       // wait for the GEMMs of the previous phase of this slot (P11 of the previous tile before E0).  Phases that also
       // read operands which do not come from those GEMMs (own bf16 chunks in shared memory, parked TMEM values) issue
@@ -1537,6 +1542,8 @@ extern "C" int pdeip_debug_tensor_trace(long long* out, int n) {
   if (cudaDeviceSynchronize() != cudaSuccess) return PDEIP_ERR_CUDA;
   if (cudaMemcpy(out, reinterpret_cast<long long*>(status) + 512, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost) !=
       cudaSuccess)
+    return PDEIP_ERR_CUDA;
+  if (cudaMemset(reinterpret_cast<long long*>(status) + 512, 0, sizeof(long long) * (size_t)n) != cudaSuccess)  // the stamps are sums
     return PDEIP_ERR_CUDA;
   return PDEIP_OK;
 }

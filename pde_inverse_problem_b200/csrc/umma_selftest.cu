@@ -278,3 +278,91 @@ extern "C" int pdeip_debug_umma_cost(int N, int reps, int variant, long long* ou
   cudaFree(d);
   return PDEIP_OK;
 }
+
+// ---- hand-off probe: warps 0..7 wait for an mbarrier that warp 8's tcgen05.commit arrives on after `reps` MMAs
+// (128 x N x 16, A from TMEM if ts).  wait_kind 0: mbarrier.try_wait spin (may suspend the thread), 1: mbarrier.test_wait
+// spin (never suspends), 2: try_wait with a suspend-time hint of `hint_ns`.  out[0] = mean cycles first issue -> commit
+// issued, out[1 + w] = mean cycles commit issued -> warp w past its wait (16 rounds, round 0 discarded). ----
+namespace pdeip {
+__global__ void __launch_bounds__(288) umma_handoff_kernel(int N, int reps, int ts, int wait_kind, uint32_t hint_ns, long long* out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t_commit[16], t_first[16], t_wake[16][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    umma::tmem_alloc(umma::smem_u32(&tmem_base_s), 512);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_u32(&mbar), 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < (kCostATile + kCostBTile) / 16; i += 288) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0x3f803f80u, 0, 0, 0);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_base_s, mb = umma::smem_u32(&mbar);
+  const uint32_t idesc = umma::make_idesc(N, 0, 0);
+  const uint64_t ad = umma::make_desc(umma::smem_u32(sm), 128u, 256u), bd = umma::make_desc(umma::smem_u32(sm) + kCostATile, 128u, 256u);
+  for (int it = 0; it < 16; ++it) {
+    const uint32_t par = it & 1;
+    asm volatile("bar.sync 1, 288;" ::: "memory");  // everybody starts the round together (the epilogue's arrive)
+    if (warp == 8) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+          if (ts) umma::mma_bf16_ts(tbase + (r & 1) * 64, tbase + 480, bd, idesc, 1u);
+          else umma::mma_bf16(tbase + (r & 1) * 64, ad, bd, idesc, 1u);
+        }
+        umma::commit(mb);
+        t_commit[it] = clock64();
+        t_first[it] = t0;
+      }
+      __syncwarp();
+    } else {
+      if (wait_kind == 0) {
+        while (!umma::mbar_try_wait(mb, par)) {}
+      } else if (wait_kind == 1) {
+        uint32_t ok = 0;
+        while (!ok)
+          asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb), "r"(par) : "memory");
+      } else {
+        uint32_t ok = 0;
+        while (!ok)
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb), "r"(par), "r"(hint_ns) : "memory");
+      }
+      umma::fence_after_sync();
+      if (lane == 0) t_wake[it][warp] = clock64();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long a = 0;
+    for (int it = 1; it < 16; ++it) a += t_commit[it] - t_first[it];
+    out[0] = a / 15;
+    for (int w = 0; w < 8; ++w) {
+      long long b = 0;
+      for (int it = 1; it < 16; ++it) b += t_wake[it][w] - t_commit[it];
+      out[1 + w] = b / 15;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+}  // namespace pdeip
+
+extern "C" int pdeip_debug_umma_handoff(int N, int reps, int ts, int wait_kind, unsigned hint_ns, long long* out_host) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 9 * 8) != cudaSuccess) return PDEIP_ERR_CUDA;
+  cudaMemset(d, 0, 72);
+  const int smem = pdeip::kCostATile + pdeip::kCostBTile + 1024;
+  pdeip::umma_handoff_kernel<<<1, 288, smem>>>(N, reps, ts, wait_kind, hint_ns, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(d); return PDEIP_ERR_CUDA; }
+  cudaMemcpy(out_host, d, 72, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return PDEIP_OK;
+}

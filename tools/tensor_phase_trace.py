@@ -25,26 +25,32 @@ torch.cuda.synchronize()
 lib = C.CDLL(L.LIB_PATH)
 lib.pdeip_debug_tensor_trace.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_longlong * 256)()
+lib.pdeip_debug_tensor_trace(buf, 256)  # discard the warm-up launches (the read clears the sums)
+acc.accumulate(L.SET_KFP_0T, flat, pts, 1.0 / n, coef=0.5, layout=layout, path=L.PATH_TENSOR, true_grad=tg)
+torch.cuda.synchronize()
 print("rc", lib.pdeip_debug_tensor_trace(buf, 256))
-t = list(buf)
+NT = 64  # kTraceTiles of residual_tensor.cu: every stamp is a sum over 64 consecutive tile rounds of CTA 0
+t = [v / NT for v in buf]
 t0 = t[0]
-print("ph s | wait_start wait_end arrive | mma_ready fast_issued all_issued   (cycles since E0(s0) wait start)")
+print("ph s | wait_start wait_end arrive | mma_ready fast_issued all_issued   (mean over 64 tiles, cycles since E0(s0) wait start)")
 for ph in range(12):
     for s in range(2):
         r = t[(ph * 2 + s) * 8:(ph * 2 + s) * 8 + 8]
         if r[0] == 0:
             continue
-        print(ph, s, "|", r[0] - t0, r[1] - t0, r[2] - t0, "|", r[4] - t0, r[5] - t0 if r[5] else '-', r[6] - t0,
-              "   wait", r[1] - r[0], "(mbar", (r[3] - r[0]) if r[3] else '-', ") epi", r[2] - r[1],
-              "(arrive", (r[2] - r[7]) if r[7] else '-', ")")
+        f = lambda x: f"{x:.0f}"
+        if r[2] == 0:  # no hand-off after this phase (kGram: E6 runs into E7)
+            print(ph, s, "|", f(r[0] - t0), f(r[1] - t0), "- | - - -    wait", f(r[1] - r[0]))
+            continue
+        print(ph, s, "|", f(r[0] - t0), f(r[1] - t0), f(r[2] - t0), "|", f(r[4] - t0), f(r[5] - t0) if r[5] else '-', f(r[6] - t0),
+              "   wait", f(r[1] - r[0]), "(mbar", f(r[3] - r[0]) if r[3] else '-', ") epi", f(r[2] - r[1]),
+              "(arrive", f(r[2] - r[7]) if r[7] else '-', ")  ready->issued", f(r[6] - r[4]), " issued->wait_end(next)")
 for s_ in range(2):
     f = t[240 + 8 * s_:240 + 8 * s_ + 8]
     r = t[(4 * 2 + s_) * 8:(4 * 2 + s_) * 8 + 8]
     if f[0]:
         print(f"E4 slot {s_}: wait-end->tmem/lds data {f[0] - r[1]}, math+STS {f[1] - f[0]}, park(st+wait) {f[2] - f[1]}, "
               f"to fence {r[7] - f[2]}, fence.proxy.async {f[3] - r[7]}, tcgen05.fence {f[4] - f[3]}, bar.arrive {r[2] - f[4]}")
-print("first mbarrier poll per (ph, slot): latency cycles / hit:",
-      [(t[192 + 2 * i], t[192 + 2 * i + 1]) for i in range(24)])
 e0 = torch.cuda.Event(enable_timing=True)
 e1 = torch.cuda.Event(enable_timing=True)
 e0.record()

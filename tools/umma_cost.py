@@ -27,3 +27,13 @@ for variant in (0, 1, 2, 16, 17, 32, 33, 48, 49, 52, 53, 64, 65, 68, 69, 18, 50)
             best = v if best is None or v[1] < best[1] else best
         row.append(f"{best[0]:5.1f}/{best[1]:5.1f}")
     print(f"variant {variant:2d}: " + "  ".join(f"N={n}: {r}" for n, r in zip((16, 32, 48, 64, 96, 128, 256), row)), " (issue / complete cycles per MMA)")
+
+# ---- hand-off latency: commit issued -> the waiting warps are past their mbarrier wait (umma_handoff_kernel) ----
+lib.pdeip_debug_umma_handoff.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+print("\nhand-off: 8 waiting warps, warp 8 issues `reps` MMAs (N = 32) + commit; cycles first issue -> commit issued | commit issued -> wake, per warp")
+for ts in (0, 1):
+    for reps in (1, 4, 10):
+        for kind, hint, name in ((0, 0, "try_wait"), (1, 0, "test_wait"), (2, 20, "try_wait hint 20 ns"), (2, 1000, "try_wait hint 1 us")):
+            buf = (C.c_longlong * 9)()
+            assert lib.pdeip_debug_umma_handoff(32, reps, ts, kind, hint, buf) == 0
+            print(f"ts={ts} reps={reps:2d} {name:22s}: issue {buf[0]:4d} | wake " + " ".join(f"{buf[1 + w]:4d}" for w in range(8)))
