@@ -77,6 +77,7 @@ constexpr uint32_t C_AB1 = C_R + 48, C_AA1R = C_R + 96;                     // P
 // (24 registers after setmaxnreg: 75 spill instructions and R2UR chains in front of the MMAs of every phase); with the
 // MMA warp on the uniform datapath the GEMM phases shorten by ~100 cycles each: d = 32 2.055e9 -> 2.24e9 evals/s.
 constexpr uint32_t C_AOP = C_SLOT0 + SLOT_COLS;  // [312, 360): columns = 4 x (chunk index within the operand)
+constexpr uint32_t C_AOPX = C_AOP + 48;           // [360, 408): the A operands of P0 ([x_hi | x_lo], v) when E0 runs a tile ahead (PIPE_X)
 
 // ---- shared memory ---------------------------------------------------------------------------------------------
 // Z tile chunk map (24 chunks of 8 columns)
@@ -94,11 +95,22 @@ struct Cfg {
   static constexpr uint32_t RG_X = NX * 128, RG_A = 12 * 128, RG_Z = 24 * 128;
   static constexpr uint32_t SZ_X = 16 * RG_X, SZ_A = 16 * RG_A, SZ_Z = 16 * RG_Z;
   static constexpr uint32_t O_X = 0, O_A1 = O_X + SZ_X, O_A2 = O_A1 + SZ_A, O_Z = O_A2 + SZ_A, SLOT = O_Z + SZ_Z;
+  // PDEIP_TC_PIPE_X (one-slot kernels; on): the x | v | g^ bands are double-buffered by tile parity, so that E0 of the
+  // NEXT tile (the bf16 hi / lo split of its inputs) runs behind E10's hand-off while P10 executes, P0 of the next tile
+  // is issued with P11 behind E11's hand-off, and the tile has 10 GEMM -> epilogue round trips instead of 11.
+#ifndef PDEIP_TC_PIPE_X
+#define PDEIP_TC_PIPE_X 1
+#endif
+#ifndef PDEIP_TC_STAGE
+#define PDEIP_TC_STAGE 0  // (see STAGE_BYTES below)
+#endif
+  static constexpr bool PIPE_X = PDEIP_TC_PIPE_X && NS == 1 && !PDEIP_TC_STAGE;
+  static constexpr uint32_t O_X2 = NS * SLOT;  // second x | v | g^ buffer (odd tiles)
   // weights (rows = output units, columns = input units), hi and lo halves
   static constexpr uint32_t RG_T0X = KX / 8 * 128, SZ_T0X = 4 * RG_T0X;
   static constexpr uint32_t RG_T0V = KV / 8 * 128, SZ_T0V = 4 * RG_T0V;
   static constexpr uint32_t RG_T1 = 512, SZ_T1 = 4 * RG_T1, RG_T2 = 512, SZ_T2 = 6 * RG_T2;
-  static constexpr uint32_t O_T0XH = NS * SLOT, O_T0XL = O_T0XH + SZ_T0X, O_T0VH = O_T0XL + SZ_T0X,
+  static constexpr uint32_t O_T0XH = NS * SLOT + (PIPE_X ? SZ_X : 0u), O_T0XL = O_T0XH + SZ_T0X, O_T0VH = O_T0XL + SZ_T0X,
                             O_T0VL = O_T0VH + SZ_T0V, O_T1H = O_T0VL + SZ_T0V, O_T1L = O_T1H + SZ_T1,
                             O_T2H = O_T1L + SZ_T1, O_T2L = O_T2H + SZ_T2,
                             // Gram tile G = c_g W0 W0^T / 8 ([32 hidden][32 hidden], hi + lo): one-slot kernels only
@@ -118,7 +130,7 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = (PDEIP_TC_STAGE && NS == 1) ? 128u * 3u * DP * 4u : 0u;
   static constexpr uint32_t O_TRUE = O_BIAS + 512, O_MISC = O_TRUE + TP_BYTES, O_STAGE = O_MISC + 128,
                             TOTAL = O_STAGE + STAGE_BYTES;
-  static_assert(TOTAL <= 227u * 1024u && O_STAGE % 128 == 0, "shared-memory budget");
+  static_assert(TOTAL <= 227u * 1024u && O_STAGE % 128 == 0 && O_X2 % 1024 == 0, "shared-memory budget");
 };
 
 #ifndef PDEIP_TC_G_CHAIN_EARLY
@@ -530,6 +542,12 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   // two-slot kernel has no shared memory for it), so that E6 and E7 run back to back and the P6 hand-off disappears:
   // 11 GEMM -> epilogue round trips per tile instead of 12, and zg^_0 no longer passes through the bf16 rounding of g^.
   constexpr bool kGram = PDEIP_TC_GRAM && NS == 1;
+  constexpr bool kPipeX = Cfg<DP, NS>::PIPE_X;  // E0 / P0 of the next tile ride behind E10 / with P11 (see Cfg)
+#ifdef PDEIP_DBG_OLDFLOW
+  constexpr bool kPipeFlow = false;
+#else
+  constexpr bool kPipeFlow = kPipeX;
+#endif
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -567,6 +585,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   }
   // every operand byte is finite from the start: zero-weight columns multiply whatever the neighbouring band holds
   for (uint32_t o = tid * 16; o < S::O_BIAS; o += kLaunchThreads * 16) *reinterpret_cast<uint4*>(sm + o) = make_uint4(0, 0, 0, 0);
+  if constexpr (S::PIPE_X)
+    for (uint32_t o = tid * 16; o < S::SZ_X; o += kLaunchThreads * 16) *reinterpret_cast<uint4*>(sm + S::O_X2 + o) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
     const float* W0 = a.params + sh.w_off(0);
@@ -646,14 +666,22 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // (26 KB): the epilogue warps are instruction-fetch sensitive and the larger MMA stream evicts their code.
     // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
     // the result is below 1e-3 (tests/tensor_v2_model.py study), the forward and input-gradient GEMMs keep hi + lo.
+#ifdef PDEIP_DBG_XB1
+    uint32_t xb = 1;
+#else
+    uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
+#endif
 #pragma unroll 1
     for (int64_t base = tile_begin; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
-      for (int ph = 0; ph < 12; ++ph) {
+      for (int ph = (kPipeFlow && base != tile_begin) ? 1 : 0; ph < 12; ++ph) {  // PIPE_X: P0 was issued with the previous P11
         if (kGram && ph == 6) continue;  // no P6: its GEMM rides in P5, its dW chain in P7
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
           const uint32_t w16 = opaque(sm16), b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4));
+          // x | v | g^ bands of the current tile / of the next one (PIPE_X: two buffers; else both are the slot's own)
+          const uint32_t x16 = kPipeX ? opaque(sm16 + (xb ? (S::O_X2 >> 4) : 0u)) : b16;
+          const uint32_t x16n = kPipeX ? opaque(sm16 + (xb ? 0u : (S::O_X2 >> 4))) : b16;
           const uint32_t TBo = opaque(TB);
           const uint32_t TS = TBo + C_SLOT0 + (uint32_t)s * SLOT_COLS;
           const uint32_t mb = smem_u32(mbar_p + s);
@@ -667,22 +695,27 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
           const Desc T0VHM = mk_desc16(w16, S::O_T0VH, S::RG_T0V, 128), T0VLM = mk_desc16(w16, S::O_T0VL, S::RG_T0V, 128);
           const Desc T1HM = mk_desc16(w16, S::O_T1H, S::RG_T1, 128), T1LM = mk_desc16(w16, S::O_T1L, S::RG_T1, 128);
           const Desc T2HM = mk_desc16(w16, S::O_T2H, S::RG_T2, 128), T2LM = mk_desc16(w16, S::O_T2L, S::RG_T2, 128);
-          const Desc XK = mk_desc16(b16, S::O_X, 128, S::RG_X), A1K = mk_desc16(b16, S::O_A1, 128, S::RG_A),
+          const Desc XK = mk_desc16(x16, S::O_X, 128, S::RG_X), A1K = mk_desc16(b16, S::O_A1, 128, S::RG_A),
                      A2K = mk_desc16(b16, S::O_A2, 128, S::RG_A), ZK = mk_desc16(b16, S::O_Z, 128, S::RG_Z);
-          const Desc XM = mk_desc16(b16, S::O_X, S::RG_X, 128), ZM = mk_desc16(b16, S::O_Z, S::RG_Z, 128);
+          const Desc XM = mk_desc16(x16, S::O_X, S::RG_X, 128), ZM = mk_desc16(b16, S::O_Z, S::RG_Z, 128);
+          const uint32_t AOPX = kPipeX ? TBo + C_AOPX : AOP;  // A operands of P0
+          // P0: z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0   (xk: K-major view of the tile's x | v bands)
+          auto issue_p0 = [&](const Desc xk) {
+            if constexpr (kTS) {
+              mm_fwd_ts<S::KX, 32, 1>({TS + C_Z0}, {AOPX}, T0XHK, T0XLK);
+              mm_fwd_ts<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, {AOPX + S::KX / 2}, T0VHK, T0VLK);
+            } else {
+              mm_fwd<S::KX, 32, 1>({TS + C_Z0}, xk, {S::XC_HI * CH}, T0XHK, T0XLK);
+              mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, xk, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
+            }
+          };
           TC_TRACE_DECL_MMA;
           mma_wait_operands(s);
           if (elect_one()) {
             TC_TRACE(4);
             switch (ph) {
-              case 0: {  // z0 = [x_hi | x_lo] [W0; W0],  z1_0 = v W0
-                if constexpr (kTS) {
-                  mm_fwd_ts<S::KX, 32, 1>({TS + C_Z0}, {AOP}, T0XHK, T0XLK);
-                  mm_fwd_ts<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, {AOP + S::KX / 2}, T0VHK, T0VLK);
-                } else {
-                  mm_fwd<S::KX, 32, 1>({TS + C_Z0}, XK, {S::XC_HI * CH}, T0XHK, T0XLK);
-                  mm_fwd<S::KV, 32, 1, (PDEIP_TC_NLO_FWD >= 2 || BND)>({TS + C_Z10}, XK, {S::XC_V * CH}, T0VHK, T0VLK);  // tangent stream
-                }
+              case 0: {
+                issue_p0(XK);
                 commit(mb);
               } break;
               case 1: {  // z1, z1_1, z2^_1
@@ -760,6 +793,12 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 commit(mb);
               } break;
               default: {  // dW0 += x_hi^T zbar0'' (+ x_lo^T zbar0'' if PDEIP_TC_XLO_DW) + g^^T za0
+                const bool p0_next = kPipeFlow && base + tile_stride < n_tiles;
+                if (p0_next) {  // PIPE_X: the next tile's x | v bands were written behind E10: its P0 goes first, the dW0
+                                // chain of this tile follows in the background (covered by the next commit)
+                  issue_p0(mk_desc16(x16n, S::O_X, 128, S::RG_X));
+                  commit(mb);
+                }
                 mm_outer<32>(TBo + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #ifdef PDEIP_TC_XLO_DW  // measured: +2 % time, no visible effect on the gradient error (x_lo = x - bf16(x) averages out)
                 mm_outer<32>(TBo + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
@@ -767,7 +806,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #if !PDEIP_TC_G_CHAIN_EARLY
                 mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
 #endif
-                commit(mb);  // the next tile's E0 overwrites the x | v bands
+                if (!p0_next) commit(mb);  // the next tile's E0 overwrites the x | v bands (PIPE_X: last tile, for the drain)
               } break;
             }
             TC_TRACE(6);
@@ -780,7 +819,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #pragma unroll 1
           for (int s = 0; s < NS; ++s) {
             const uint32_t b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4)), TBo = opaque(TB);
-            const Desc XM = mk_desc16(b16, S::O_X, S::RG_X, 128), A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128),
+            const uint32_t x16 = kPipeX ? opaque(sm16 + (xb ? (S::O_X2 >> 4) : 0u)) : b16;
+            const Desc XM = mk_desc16(x16, S::O_X, S::RG_X, 128), A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128),
                        A2M = mk_desc16(b16, S::O_A2, S::RG_A, 128), ZM = mk_desc16(b16, S::O_Z, S::RG_Z, 128);
             const uint32_t acc_first = (dw_started | (uint32_t)s) ? 1u : 0u;
             if (elect_one()) {
@@ -811,6 +851,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
       }
       dw_started = 1u;
+      xb ^= 1u;
     }
   } else if (warp < kEpiThreads / 32) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs<NS>::kEpi));
@@ -842,7 +883,28 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // prefetched input chunks: item j = half + 2 i;  j in [0, XC): x chunk j;  [XC, 2 XC): v;  [2 XC, 3 XC): stored gt
     constexpr int NI = (3 * S::XC + 1) / 2;
     float xin0[NI][8], xin1[NI][8];
+    // BLOCK128 point sets with d == DP (the pipeline's layout and the benchmark widths): the tile is one block of
+    // [dimw][128] floats, so every component of this thread's row sits at a COMPILE-TIME offset from one base pointer:
+    // 48 loads with immediate offsets at d = 32 instead of ~12 instructions of 64-bit index arithmetic per load (the
+    // generic path below: 560 instructions and ~2.3 k cycles per tile in the phase trace).
+    const bool fast_in = !FPM && a.layout == PDEIP_LAYOUT_BLOCK128 && d == DP;
     auto load_into = [&](float (&xin)[NI][8], int64_t t) {
+      if (fast_in) {
+        const int64_t pp = t * 128 + row;
+        const bool inside = t < n_tiles && pp < a.n_points;
+        // item j = half + 2 i holds components [8 j, 8 j + 8) of the row (band j / XC, chunk j % XC, DP = 8 XC): the
+        // runtime half goes into the base pointer, the rest is an immediate
+        const float* const pb = a.points + (inside ? t * (int64_t)(128 * dimw) + row : (int64_t)0) + half * (8 * 128);
+        const bool has_gt = a.tg.kind == PDEIP_DRIFT_IN_POINTS;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          if (half + 2 * i >= 3 * S::XC) continue;       // (d = 8: the fourth item does not exist)
+          if (half + 2 * i >= 2 * S::XC && !has_gt) continue;  // stored true gradient: only if the rows carry it
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xin[i][e] = __ldg(pb + (16 * i + e) * 128);
+        }
+        return;
+      }
       const int64_t cstride = comp_stride(a.layout, a.n_points);
       // FP: virtual tile -> (point tile, direction); tile counts stay below 2^31
       const uint32_t tq = FPM ? (uint32_t)t / fpd : 0u;
@@ -913,13 +975,43 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 
     bool first = true;
     int64_t base = tile_begin;
+#ifdef PDEIP_DBG_XB1
+    uint32_t xb = 1;
+#else
+    uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
+#endif
+    const uint32_t LOPX = kPipeX ? TB + ((uint32_t)(q * 32) << 16) + C_AOPX : LOP;  // this thread's lane of P0's A-operand columns
+    // E0: x (hi + lo) and v bands of a tile from its prefetched inputs (Xd: this thread's row of the destination buffer)
+    auto emit_x = [&](const float (&xin)[NI][8], const bool valid_t, uint8_t* const Xd) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int j = half + 2 * i;
+        const int band = j / S::XC, cg = j % S::XC;
+        if (band == 0) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xv = (valid_t && cg * 8 + e < d) ? xin[i][e] : 0.f;
+            hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
+            lo[e] = xv - hi[e];
+          }
+          put_op<kTS>(Xd, (S::XC_HI + cg) * 128, LOPX + 4 * cg, hi);
+          put_op<kTS>(Xd, (S::XC_LO + cg) * 128, LOPX + 4 * (S::XC + cg), lo);
+        } else if (band == 1) {
+          float vv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) vv[e] = (valid_t && cg * 8 + e < d) ? xin[i][e] : 0.f;
+          put_op<kTS>(Xd, (S::XC_V + cg) * 128, LOPX + S::KX / 2 + 4 * cg, vv);
+        }
+      }
+    };
 
     // one epilogue phase of one slot: wait for the previous GEMM phase of that slot, compute, signal the MMA warp
     // The phase bodies are shared by the two slots (runtime slot offsets): E_k(slot 0) and E_k(slot 1) run back to
     // back on the same ~20 KB of instructions, so the second pass is served by the instruction cache.
     auto phase = [&](auto PHc, const int s) {
       constexpr int ph = decltype(PHc)::value;
-      uint8_t* const X = sm + (uint32_t)s * S::SLOT + S::O_X + offX;
+      uint8_t* const X = sm + (kPipeX ? (xb ? S::O_X2 : 0u) : (uint32_t)s * S::SLOT) + S::O_X + offX;
       uint8_t* const A1 = sm + (uint32_t)s * S::SLOT + S::O_A1 + offA;
       uint8_t* const A2 = sm + (uint32_t)s * S::SLOT + S::O_A2 + offA;
       uint8_t* const Z = sm + (uint32_t)s * S::SLOT + S::O_Z + offZ;
@@ -984,31 +1076,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       }
       if constexpr (ph <= 3 || ph == 6 || !kEarlyLoads) wait_gemm();
       if constexpr (ph == 0) {  // E0: x (hi + lo) and v bands of this tile
-        auto emit = [&](const float (&xin)[NI][8]) {
-#pragma unroll
-          for (int i = 0; i < NI; ++i) {
-            const int j = half + 2 * i;
-            const int band = j / S::XC, cg = j % S::XC;
-            if (band == 0) {
-              float hi[8], lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float xv = (valid && cg * 8 + e < d) ? xin[i][e] : 0.f;
-                hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
-                lo[e] = xv - hi[e];
-              }
-              put_op<kTS>(X, (S::XC_HI + cg) * 128, LOP + 4 * cg, hi);
-              put_op<kTS>(X, (S::XC_LO + cg) * 128, LOP + 4 * (S::XC + cg), lo);
-            } else if (band == 1) {
-              float vv[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) vv[e] = (valid && cg * 8 + e < d) ? xin[i][e] : 0.f;
-              put_op<kTS>(X, (S::XC_V + cg) * 128, LOP + S::KX / 2 + 4 * cg, vv);
-            }
-          }
-        };
-        if (NS == 2 && s == 1) emit(xin1);
-        else emit(xin0);
+        if (NS == 2 && s == 1) emit_x(xin1, valid, X);
+        else emit_x(xin0, valid, X);
       } else if constexpr (ph == 1 || ph == 2) {
         // E1: t1, a1_1 = s1 z1, a2^_1 = t a1 z1      E2: t2, a1_2, a2^_2 = s1 z2^ + t a1 z1     (a2^ = -a2 / 2)
         constexpr bool l1 = ph == 1;
@@ -1112,6 +1181,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         TC_PROBE(7, u24, sv, 24);
         TC_PROBE(8, u24, sp, 24);
       } else if constexpr (ph == 4 || ph == 5) {
+        if constexpr (kPipeFlow && ph == 4) prefetch_inputs(tile + tile_stride);  // read behind E10's hand-off
         // E4 (hidden layer 2) / E5 (hidden layer 1):  aa^ = 4 aa from the GEMM of za^
         //   za^' = aa^ s1,  zbar1' = s1 ab1 + 2 t aa^ a1,  pz = a1 (aa^ a1 - 2 t ab1)
         constexpr bool l2 = ph == 4;
@@ -1283,7 +1353,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // blocking load)
 #if PDEIP_TC_L2_PREFETCH
         if constexpr (l2) {
-          if (!use_stage) prefetch_inputs(tile + tile_stride);
+          if constexpr (kPipeFlow) {  // (the next tile's inputs are read behind this phase's hand-off, see below; their
+                                      // L2 prefetch was issued in E4)
+          } else if (!use_stage) {
+            prefetch_inputs(tile + tile_stride);
+          }
         }
 #else
         if constexpr (l2) load_inputs(s, tile + tile_stride);
@@ -1342,15 +1416,29 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
         TC_TRACE(2);
       }
+      if constexpr (kPipeFlow && ph == 10) {  // E0 of the NEXT tile, while P10 executes (its TMEM stores and shared-memory
+                                          // writes are ordered before P0 by the wait::st / proxy fence of E11's hand-off)
+        // The inputs were pulled into L2 one tile ago; the loads are issued HERE and not at the start of E10: with the
+        // 48 input registers live across E10 the compiler parks them in local memory, and the store behind each load
+        // sits out the full memory latency in front of the wait for P9 (phase trace: +1.8 k cycles per tile at d = 32).
+        const int64_t tn = tile + tile_stride;
+        const int64_t pn = (FPM ? (int64_t)((uint32_t)tn / fpd) : tn) * 128 + row;
+        if (tn < n_tiles) {
+          load_inputs(s, tn);
+          emit_x(xin0, pn < a.n_points, sm + (xb ? 0u : S::O_X2) + S::O_X + offX);
+        }
+      }
     };
 #define PDEIP_TC_PHASE(PH)                       \
   _Pragma("unroll 1") for (int s_ = 0; s_ < NS; ++s_) phase(IC<PH>{}, s_);
 
 #pragma unroll 1
     for (; base < n_tiles; base += tile_stride) {
-      PDEIP_TC_PHASE(0) PDEIP_TC_PHASE(1) PDEIP_TC_PHASE(2) PDEIP_TC_PHASE(3) PDEIP_TC_PHASE(4) PDEIP_TC_PHASE(5)
+      if (!kPipeFlow || first) { PDEIP_TC_PHASE(0) }
+      PDEIP_TC_PHASE(1) PDEIP_TC_PHASE(2) PDEIP_TC_PHASE(3) PDEIP_TC_PHASE(4) PDEIP_TC_PHASE(5)
       PDEIP_TC_PHASE(6) PDEIP_TC_PHASE(7) PDEIP_TC_PHASE(8) PDEIP_TC_PHASE(9) PDEIP_TC_PHASE(10) PDEIP_TC_PHASE(11)
       first = false;
+      xb ^= 1u;
     }
 #undef PDEIP_TC_PHASE
     // ---- drain: wait for P11 of the last tile of every slot (covers every MMA issued before it) --------------

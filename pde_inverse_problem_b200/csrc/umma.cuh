@@ -118,6 +118,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t saddr, uint32_t parity) {
 // Bounded wait: returns false if the phase did not complete within ~`budget` polls (a wrong descriptor must
 // not hang the GPU box; the caller records the failure and bails out).
 __device__ __forceinline__ bool mbar_wait(uint32_t saddr, uint32_t parity, uint32_t budget = (1u << 24)) {
+#pragma unroll 1  // (the compiler unrolled this 64 x at every wait site: ~3 KB of code each)
   for (uint32_t i = 0; i < budget; ++i)
     if (mbar_try_wait(saddr, parity)) return true;
   return false;

@@ -79,10 +79,12 @@ def test_tensor_path_matches_oracle(cuda, d, n):
             off += leaf.numel()
 
 
-def test_tensor_path_matches_fp32_path_many_tiles(cuda):
-    """More tiles than CTAs (persistent loop, TMEM-persistent bias regions), SoA layout, GMM true gradient."""
+@pytest.mark.parametrize("d,tiles,layout_name", [(8, 3, "soa"), (16, 4, "soa"), (32, 3, "soa"), (32, 5, "aos"), (16, 2, "aos")])
+def test_tensor_path_matches_fp32_path_many_tiles(cuda, d, tiles, layout_name):
+    """More tiles than CTAs (persistent loop, TMEM-persistent dW regions; one-slot kernels d > 8: the steady state in
+    which E0 / P0 of the next tile ride behind E10 / with P11 on the second x | v | g^ buffer), GMM true gradient."""
     ops, L = _ops()
-    d, K, n = 8, 16, 148 * 128 * 3 + 517
+    K, n = 16, 148 * 128 * tiles + 517
     p = _params(d)
     flat = o_model.flatten_params(p).float().to(cuda)
     g = torch.Generator().manual_seed(9)
@@ -91,12 +93,14 @@ def test_tensor_path_matches_fp32_path_many_tiles(cuda):
     tg = ops.TrueGrad(L.DRIFT_GMM, mus, 1.0)
     spec = ops.ModelSpec(L.MODEL_MLP, d, 32, 2)
     s32, g32 = _run(ops, L, cuda, spec, flat, pts, n, 0.5, tg, L.PATH_FP32)
-    stc, gtc = _run(ops, L, cuda, spec, flat, pts.t().contiguous(), n, 0.5, tg, L.PATH_TENSOR, layout=L.LAYOUT_SOA)
+    layout = L.LAYOUT_SOA if layout_name == "soa" else L.LAYOUT_AOS
+    pts_t = pts.t().contiguous() if layout_name == "soa" else pts
+    stc, gtc = _run(ops, L, cuda, spec, flat, pts_t, n, 0.5, tg, L.PATH_TENSOR, layout=layout)
     assert relmax(stc[L.SUM_LOSS], s32[L.SUM_LOSS]) < TOL
     assert relmax(stc[L.SUM_GT], s32[L.SUM_GT]) < TOL
     assert relmax(gtc, g32) < TOL
     # run twice: bit-identical (no atomics across CTAs, fixed reduction order)
-    stc2, gtc2 = _run(ops, L, cuda, spec, flat, pts.t().contiguous(), n, 0.5, tg, L.PATH_TENSOR, layout=L.LAYOUT_SOA)
+    stc2, gtc2 = _run(ops, L, cuda, spec, flat, pts_t, n, 0.5, tg, L.PATH_TENSOR, layout=layout)
     assert torch.equal(gtc, gtc2)
 
 
