@@ -741,7 +741,10 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
               case 5: {  // g = za0 W0^T;  dW0 += v^T zbar1''
                 if constexpr (kTS) mm_bwd_ts<32, S::KV, 1>({TS + C_G}, {AOP}, T0VHM, T0VLM, S::RG_T0V);
                 else mm_bwd<32, S::KV, 1>({TS + C_G}, ZK, {ZC_ZA0 * CH}, T0VHM, T0VLM, S::RG_T0V);
-                if constexpr (kGram) mm_fwd<32, 32, 1, true>({TS + C_ZG0}, ZK, {ZC_ZA0 * CH}, TGHK, TGLK);  // zg^_0
+                if constexpr (kGram) {  // zg^_0 (the same A operand as the g GEMM)
+                  if constexpr (kTS) mm_fwd_ts<32, 32, 1, true>({TS + C_ZG0}, {AOP}, TGHK, TGLK);
+                  else mm_fwd<32, 32, 1, true>({TS + C_ZG0}, ZK, {ZC_ZA0 * CH}, TGHK, TGLK);
+                }
                 commit(mb);
               } break;
               case 6: {  // zg^_0 = g^ W0
