@@ -207,8 +207,9 @@ constexpr int kTraceTiles = 64;
 #endif
 
 // epilogue side: operands written -> visible to the tensor core; TMEM accesses ordered; signal the MMA warp
+template <bool PROXY_FENCE = true>
 __device__ __forceinline__ void epi_arrive(int slot) {
-  fence_async_smem();
+  if constexpr (PROXY_FENCE) fence_async_smem();
   fence_before_sync();
   asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "n"(kThreads) : "memory");
 }
@@ -1415,7 +1416,12 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         TC_FINE(4);
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(kThreads) : "memory");
 #else
-        epi_arrive(s);
+        // The generic -> async proxy fence orders this thread's shared-memory writes before the MMAs that READ them.  With
+        // the layer-GEMM A operands in TMEM (kTS) the GEMMs of P0, P1, P2 and P8 read no activation bytes from shared
+        // memory, and the bands written by E0, E1, E2, E8 are first read by dW chains issued behind LATER hand-offs
+        // (P3 / P4 / P5 / P9 ...), whose fences (same thread, later in program order) cover these writes too.
+        constexpr bool kNeedProxyFence = !(kTS && (ph == 0 || ph == 1 || ph == 2 || ph == 8));
+        epi_arrive<kNeedProxyFence>(s);
 #endif
         TC_TRACE(2);
       }
