@@ -543,6 +543,14 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
   // two-slot kernel has no shared memory for it), so that E6 and E7 run back to back and the P6 hand-off disappears:
   // 11 GEMM -> epilogue round trips per tile instead of 12, and zg^_0 no longer passes through the bf16 rounding of g^.
   constexpr bool kGram = PDEIP_TC_GRAM && NS == 1;
+  // Two-stage hand-off (one-slot kernels with the A operands in TMEM): the layer GEMMs of a phase read TMEM and the
+  // weights only, so they are released by a first arrive right behind tcgen05.wait::st; the generic -> async proxy fence,
+  // which only the dW chains of the phase need (they read the activation bands from shared memory), follows on a second
+  // named barrier while the layer GEMMs already execute.
+#ifndef PDEIP_TC_TWO_STAGE
+#define PDEIP_TC_TWO_STAGE 1
+#endif
+  constexpr bool kTwoStage = PDEIP_TC_TWO_STAGE && kTS;
   constexpr bool kPipeX = Cfg<DP, NS>::PIPE_X;  // E0 / P0 of the next tile ride behind E10 / with P11 (see Cfg)
 #ifdef PDEIP_DBG_OLDFLOW
   constexpr bool kPipeFlow = false;
@@ -762,7 +770,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                 if constexpr (kTS) mm_fwd_ts<32, 32, 1, false>({TS + C_ZG1}, {AOP}, T1HK, T1LK);
                 else mm_fwd<32, 32, 1, false>({TS + C_ZG1}, A1K, {AC_A1 * CH}, T1HK, T1LK);
                 commit(mb);
-                if constexpr (kGram)  // dW0 += g^^T za0 (P6's chain; g^ was written in E6, ordered by E7's arrive)
+                if constexpr (kGram && !kTwoStage)  // dW0 += g^^T za0 (P6's chain; g^ was written in E6, ordered by E7's arrive)
                   mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
                 if constexpr (kCChainsEarly) {  // dW1 += c_1^T za1: c_1 is final since E7 (just arrived), za1 since E4
                   const Desc A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128);
@@ -803,14 +811,16 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                   issue_p0(mk_desc16(x16n, S::O_X, 128, S::RG_X));
                   commit(mb);
                 }
-                mm_outer<32>(TBo + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                if constexpr (!kTwoStage) {  // (two-stage hand-off: the chain is issued behind the second barrier, below)
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #ifdef PDEIP_TC_XLO_DW  // measured: +2 % time, no visible effect on the gradient error (x_lo = x - bf16(x) averages out)
-                mm_outer<32>(TBo + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
 #endif
 #if !PDEIP_TC_G_CHAIN_EARLY
-                mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
 #endif
-                if (!p0_next) commit(mb);  // the next tile's E0 overwrites the x | v bands (PIPE_X: last tile, for the drain)
+                  if (!p0_next) commit(mb);  // the next tile's E0 overwrites the x | v bands (PIPE_X: last tile, for the drain)
+                }
               } break;
             }
             TC_TRACE(6);
@@ -819,9 +829,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         }
         // background (batch-reduced dW) GEMMs of this phase, issued after the fast GEMMs of BOTH slots so that the
         // second slot's fast GEMMs do not queue behind the first slot's dW chains (the tensor pipe runs in issue order)
-        if (ph == 3 || ph == 4 || ph == 5 || ph == 9 || ph == 10) {
+        if (ph == 3 || ph == 4 || ph == 5 || ph == 9 || ph == 10 || (kTwoStage && (ph == 7 || ph == 11))) {
 #pragma unroll 1
           for (int s = 0; s < NS; ++s) {
+            if constexpr (kTwoStage) {  // second stage of the hand-off: the activation bands are visible to the async proxy
+              asm volatile("bar.sync %0, %1;" ::"r"(4 + s), "n"(kThreads) : "memory");
+              fence_after_sync();
+            }
             const uint32_t b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4)), TBo = opaque(TB);
             const uint32_t x16 = kPipeX ? opaque(sm16 + (xb ? (S::O_X2 >> 4) : 0u)) : b16;
             const Desc XM = mk_desc16(x16, S::O_X, S::RG_X, 128), A1M = mk_desc16(b16, S::O_A1, S::RG_A, 128),
@@ -843,11 +857,24 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
                   if constexpr (!kCChainsEarly)
                     mm_outer<OP>(TBo + C_DW2, A2M, AC_C * CH, S::RG_A, ZM, ZC_ZA2 * CH, S::RG_Z, 1u);
                   break;
-                default:  // dW1 += t1^T zbar0' + c_1^T za1
+                case 10:  // dW1 += t1^T zbar0' + c_1^T za1
                   mm_outer<32>(TBo + C_DW1, A1M, AC_T * CH, S::RG_A, ZM, ZC_TB * CH, S::RG_Z, 1u);
                   if constexpr (!kCChainsEarly)
                     mm_outer<32>(TBo + C_DW1, A1M, AC_C * CH, S::RG_A, ZM, ZC_ZA1 * CH, S::RG_Z, 1u);
                   break;
+                case 7:  // (two-stage hand-off) dW0 += g^^T za0: P6's chain, g^ written in E6 and fenced in E7
+                  if constexpr (kGram) mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+                  break;
+                default: {  // (two-stage hand-off) P11: dW0 += x_hi^T zbar0''; the drain's commit on the last tile
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_HI * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+#ifdef PDEIP_TC_XLO_DW
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_LO * CH, S::RG_X, ZM, ZC_TA * CH, S::RG_Z, 1u);
+#endif
+#if !PDEIP_TC_G_CHAIN_EARLY
+                  mm_outer<32>(TBo + C_DW0, XM, S::XC_G * CH, S::RG_X, ZM, ZC_ZA0 * CH, S::RG_Z, 1u);
+#endif
+                  if (!(kPipeFlow && base + tile_stride < n_tiles)) commit(smem_u32(mbar_p + s));
+                } break;
               }
             }
             __syncwarp();
@@ -1409,6 +1436,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       if constexpr (!(kGram && ph == 6)) {  // kGram: no hand-off after E6, E7 follows immediately (zg^_0 came out of P5)
         if constexpr (kTS) tm_wait_st();  // the A-operand columns are complete before the hand-off
         TC_TRACE(7);
+        if constexpr (kTwoStage && (ph == 3 || ph == 4 || ph == 5 || ph == 7 || ph == 9 || ph == 10 || ph == 11)) {
+          epi_arrive<false>(s);  // layer GEMMs (A from TMEM, B = weights): go
+          fence_async_smem();    // the bands this phase wrote -> async proxy, for the dW chains behind the second barrier
+          asm volatile("bar.arrive %0, %1;" ::"r"(4 + s), "n"(kThreads) : "memory");
+        } else {
 #ifdef PDEIP_TC_TRACE
         fence_async_smem();
         TC_FINE(3);
@@ -1423,6 +1455,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         constexpr bool kNeedProxyFence = !(kTS && (ph == 0 || ph == 1 || ph == 2 || ph == 8));
         epi_arrive<kNeedProxyFence>(s);
 #endif
+        }
         TC_TRACE(2);
       }
       if constexpr (kPipeFlow && ph == 10) {  // E0 of the NEXT tile, while P10 executes (its TMEM stores and shared-memory
