@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // 48 loads with immediate offsets at d = 32 instead of ~12 instructions of 64-bit index arithmetic per load (the
     // generic path below: 560 instructions and ~2.3 k cycles per tile in the phase trace).
     const bool fast_in = !FPM && a.layout == PDEIP_LAYOUT_BLOCK128 && d == DP;
-    auto load_into = [&](float (&xin)[NI][8], int64_t t) {
+    auto load_into = [&](float (&xin)[NI][8], int64_t t, const int i0 = 0, const int i1 = 64) {  // items [i0, i1)
       if (fast_in) {
         const int64_t pp = t * 128 + row;
         const bool inside = t < n_tiles && pp < a.n_points;
@@ -929,6 +929,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const bool has_gt = a.tg.kind == PDEIP_DRIFT_IN_POINTS;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
+          if (i < i0 || i >= i1) continue;
           if (half + 2 * i >= 3 * S::XC) continue;       // (d = 8: the fourth item does not exist)
           if (half + 2 * i >= 2 * S::XC && !has_gt) continue;  // stored true gradient: only if the rows carry it
 #pragma unroll
@@ -945,6 +946,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
       const float* const pbase = a.points + point_base(a.layout, pc, dimw);
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
+        if (i < i0 || i >= i1) continue;
         const int j = half + 2 * i;
         const int band = (j / S::XC) < 3 ? (j / S::XC) : 0, cg = j % S::XC;
         const int bandc = (band < 2 || a.tg.kind == PDEIP_DRIFT_IN_POINTS) ? band : 0;
@@ -974,9 +976,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     };
     if (use_stage && tid == 0) stage_issue(tile_begin);
     // two separate branches: each slot's loads target its own registers directly (no select on the loaded value)
-    auto load_inputs = [&](int s, int64_t t) {
-      if (NS == 2 && s == 1) load_into(xin1, t);
-      else load_into(xin0, t);
+    auto load_inputs = [&](int s, int64_t t, const int i0 = 0, const int i1 = 64) {
+      if (NS == 2 && s == 1) load_into(xin1, t, i0, i1);
+      else load_into(xin0, t, i0, i1);
     };
 #ifndef PDEIP_TC_L2_PREFETCH
 #define PDEIP_TC_L2_PREFETCH 1
@@ -1384,8 +1386,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // blocking load)
 #if PDEIP_TC_L2_PREFETCH
         if constexpr (l2) {
-          if constexpr (kPipeFlow) {  // (the next tile's inputs are read behind this phase's hand-off, see below; their
-                                      // L2 prefetch was issued in E4)
+          if constexpr (kPipeFlow) {  // the next tile's x items (16 registers; L2 prefetch issued in E4) are read here and
+                                      // land behind this phase; the rest is read behind its hand-off, see below
+            if (tile + tile_stride < n_tiles) load_inputs(s, tile + tile_stride, 0, S::XC / 2);
           } else if (!use_stage) {
             prefetch_inputs(tile + tile_stride);
           }
@@ -1466,7 +1469,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const int64_t tn = tile + tile_stride;
         const int64_t pn = (FPM ? (int64_t)((uint32_t)tn / fpd) : tn) * 128 + row;
         if (tn < n_tiles) {
-          load_inputs(s, tn);
+          load_inputs(s, tn, S::XC / 2, 64);
           emit_x(xin0, pn < a.n_points, sm + (xb ? 0u : S::O_X2) + S::O_X + offX);
         }
       }
