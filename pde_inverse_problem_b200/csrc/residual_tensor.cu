@@ -1386,9 +1386,11 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         // blocking load)
 #if PDEIP_TC_L2_PREFETCH
         if constexpr (l2) {
-          if constexpr (kPipeFlow) {  // the next tile's x items (16 registers; L2 prefetch issued in E4) are read here and
-                                      // land behind this phase; the rest is read behind its hand-off, see below
-            if (tile + tile_stride < n_tiles) load_inputs(s, tile + tile_stride, 0, S::XC / 2);
+          if constexpr (kPipeFlow) {  // the first two items of the next tile (16 registers: x at d = 32, x and v at d = 16;
+                                      // L2 prefetch issued in E4) are read here and land behind this phase; the rest is read
+                                      // behind its hand-off, see below (measured: more than 16 registers here costs more
+                                      // in E10 than the hidden latency gives back)
+            if (tile + tile_stride < n_tiles) load_inputs(s, tile + tile_stride, 0, 2);
           } else if (!use_stage) {
             prefetch_inputs(tile + tile_stride);
           }
@@ -1469,7 +1471,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         const int64_t tn = tile + tile_stride;
         const int64_t pn = (FPM ? (int64_t)((uint32_t)tn / fpd) : tn) * 128 + row;
         if (tn < n_tiles) {
-          load_inputs(s, tn, S::XC / 2, 64);
+          load_inputs(s, tn, 2, 64);
           emit_x(xin0, pn < a.n_points, sm + (xb ? 0u : S::O_X2) + S::O_X + offX);
         }
       }
