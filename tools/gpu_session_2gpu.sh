@@ -1,11 +1,8 @@
 #!/bin/bash
-# 2-GPU session: strong scaling of the default C5 bench, the interacting (mean-field) system at 1 and 2 ranks
+# 2-GPU session: strong scaling of the default C5 bench, the interacting (mean-field) system at 2 ranks
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $TR bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_C5_2gpu.json 2> gpurun_out/bench_C5_2gpu.err; echo "rc=$?" >> gpurun_out/bench_C5_2gpu.err
 timeout 600 $TR bench.py --gpus 2 --steps 5 --warmup 3 --workload C4mf > gpurun_out/bench_C4mf_2gpu.json 2> gpurun_out/bench_C4mf_2gpu.err; echo "rc=$?" >> gpurun_out/bench_C4mf_2gpu.err
-timeout 600 python bench.py --steps 5 --warmup 3 --workload C4mf --no-cpu-baseline > gpurun_out/bench_C4mf_1gpu.json 2> gpurun_out/bench_C4mf_1gpu.err; echo "rc=$?" >> gpurun_out/bench_C4mf_1gpu.err
-timeout 600 python bench.py --steps 5 --warmup 3 --workload C4 --no-cpu-baseline > gpurun_out/bench_C4_1gpu.json 2> gpurun_out/bench_C4_1gpu.err; echo "rc=$?" >> gpurun_out/bench_C4_1gpu.err
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/bench_C5_1gpu_samebox.json 2> gpurun_out/bench_C5_1gpu_samebox.err
-tail -3 gpurun_out/*.err
+tail -n 3 gpurun_out/bench_C5_2gpu.err gpurun_out/bench_C4mf_2gpu.err
