@@ -105,7 +105,11 @@ struct Cfg {
 #define PDEIP_TC_STAGE 0  // (see STAGE_BYTES below)
 #endif
   static constexpr bool PIPE_X = PDEIP_TC_PIPE_X && NS == 1 && !PDEIP_TC_STAGE;
-  static constexpr uint32_t O_X2 = NS * SLOT;  // second x | v | g^ buffer (odd tiles)
+  // second x | v | g^ buffer (odd tiles).  It sits between the slot and the weights, NOT at the end of the allocation: the
+  // M = 64 band-shifted dW chains read 64 operand columns from the start of a band, i.e. up to (8 - XC) x 128 B past the
+  // last row group of the tile (the cross-term rows that nobody reads) — harmless while something is mapped behind the
+  // tile, an illegal-address fault when the tile is the last thing in shared memory (measured).
+  static constexpr uint32_t O_X2 = NS * SLOT;
   // weights (rows = output units, columns = input units), hi and lo halves
   static constexpr uint32_t RG_T0X = KX / 8 * 128, SZ_T0X = 4 * RG_T0X;
   static constexpr uint32_t RG_T0V = KV / 8 * 128, SZ_T0V = 4 * RG_T0V;
