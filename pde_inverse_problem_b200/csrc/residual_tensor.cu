@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #else
     uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
 #endif
+    uint32_t tsb = 0;  // two-stage hand-off: which of the two second-stage barriers is next
 #pragma unroll 1
     for (int64_t base = tile_begin; base < n_tiles; base += tile_stride) {
 #pragma unroll 1
@@ -836,8 +837,13 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         if (ph == 3 || ph == 4 || ph == 5 || ph == 9 || ph == 10 || (kTwoStage && (ph == 7 || ph == 11))) {
 #pragma unroll 1
           for (int s = 0; s < NS; ++s) {
-            if constexpr (kTwoStage) {  // second stage of the hand-off: the activation bands are visible to the async proxy
-              asm volatile("bar.sync %0, %1;" ::"r"(4 + s), "n"(kThreads) : "memory");
+            if constexpr (kTwoStage) {  // second stage of the hand-off: the activation bands are visible to the async proxy.
+              // TWO named barriers (4, 5) used alternately: the epilogue's next second-stage arrive follows its wait for
+              // this phase's commit, which is issued BEFORE this barrier — with a single barrier a slow MMA warp could
+              // be overtaken (two generations of arrivals on one barrier: a deadlock seen once in ~1e4 launches).  With
+              // two, the arrive after next needs the commit of the next phase, which this warp issues behind this sync.
+              asm volatile("bar.sync %0, %1;" ::"r"(4 + (int)tsb), "n"(kThreads) : "memory");
+              tsb ^= 1u;
               fence_after_sync();
             }
             const uint32_t b16 = opaque(sm16 + (uint32_t)s * (S::SLOT >> 4)), TBo = opaque(TB);
@@ -1017,6 +1023,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #else
     uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
 #endif
+    uint32_t tsb = 0;  // two-stage hand-off: which of the two second-stage barriers is next
     const uint32_t LOPX = kPipeX ? TB + ((uint32_t)(q * 32) << 16) + C_AOPX : LOP;  // this thread's lane of P0's A-operand columns
     // E0: x (hi + lo) and v bands of a tile from its prefetched inputs (Xd: this thread's row of the destination buffer)
     auto emit_x = [&](const float (&xin)[NI][8], const bool valid_t, uint8_t* const Xd) {
@@ -1448,7 +1455,8 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
         if constexpr (kTwoStage && (ph == 3 || ph == 4 || ph == 5 || ph == 7 || ph == 9 || ph == 10 || ph == 11)) {
           epi_arrive<false>(s);  // layer GEMMs (A from TMEM, B = weights): go
           fence_async_smem();    // the bands this phase wrote -> async proxy, for the dW chains behind the second barrier
-          asm volatile("bar.arrive %0, %1;" ::"r"(4 + s), "n"(kThreads) : "memory");
+          asm volatile("bar.arrive %0, %1;" ::"r"(4 + (int)tsb), "n"(kThreads) : "memory");
+          tsb ^= 1u;
         } else {
 #ifdef PDEIP_TC_TRACE
         fence_async_smem();
