@@ -556,11 +556,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 #endif
   constexpr bool kTwoStage = PDEIP_TC_TWO_STAGE && kTS;
   constexpr bool kPipeX = Cfg<DP, NS>::PIPE_X;  // E0 / P0 of the next tile ride behind E10 / with P11 (see Cfg)
-#ifdef PDEIP_DBG_OLDFLOW
-  constexpr bool kPipeFlow = false;
-#else
-  constexpr bool kPipeFlow = kPipeX;
-#endif
+  constexpr bool kPipeFlow = kPipeX;  // the schedule that goes with the second buffer
   using S = Cfg<DP, NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -679,11 +675,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
     // (26 KB): the epilogue warps are instruction-fetch sensitive and the larger MMA stream evicts their code.
     // The lo halves of the weights are skipped for the g-stream (P6..P8) and adjoint (P9, P10) GEMMs: their effect on
     // the result is below 1e-3 (tests/tensor_v2_model.py study), the forward and input-gradient GEMMs keep hi + lo.
-#ifdef PDEIP_DBG_XB1
-    uint32_t xb = 1;
-#else
     uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
-#endif
     uint32_t tsb = 0;  // two-stage hand-off: which of the two second-stage barriers is next
 #pragma unroll 1
     for (int64_t base = tile_begin; base < n_tiles; base += tile_stride) {
@@ -1018,11 +1010,7 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) mlp_residual_tc_kernel(cons
 
     bool first = true;
     int64_t base = tile_begin;
-#ifdef PDEIP_DBG_XB1
-    uint32_t xb = 1;
-#else
     uint32_t xb = 0;  // PIPE_X: which x | v | g^ buffer holds the current tile
-#endif
     uint32_t tsb = 0;  // two-stage hand-off: which of the two second-stage barriers is next
     const uint32_t LOPX = kPipeX ? TB + ((uint32_t)(q * 32) << 16) + C_AOPX : LOP;  // this thread's lane of P0's A-operand columns
     // E0: x (hi + lo) and v bands of a tile from its prefetched inputs (Xd: this thread's row of the destination buffer)
